@@ -1,0 +1,718 @@
+// engine.cu -- the step driver: B200-native counterpart of GmpmSimulator (reference
+// Projects/GMPM/gmpm_simulator.cuh:23-786) and of one MgspBenchmark device worker
+// (Projects/MGSP/mgsp_benchmark.cuh:156-776).
+//
+// What differs from the reference driver, by design:
+//   * block counts, bin counts, dt, max velocity and the frame clock live in a device-resident StepState; the
+//     reference copies seven counters to the host and synchronises after each (gmpm_simulator.cuh:344,462,502,
+//     517,541,564 + syncStream), here a sub-step is a fixed sequence of launches with no host round trip;
+//   * that sequence is captured once per roll parity into a CUDA graph and replayed;
+//   * every kernel runs on a persistent grid sized from the SM count and loops over device-read counts;
+//   * clears, marks, bucket compaction and the grid carry are fused as described in partition.cuh / grid.cuh.
+// Not built in this compiled library: file IO (the async .bgeo writer thread).  The JSON scene loader lives in
+// the Python host layer (claymore_b200/scene.py).
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "g2p2g.cuh"
+#include "grid.cuh"
+#include "init.cuh"
+#include "partition.cuh"
+
+namespace cb200 {
+int num_sms();
+cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaStream_t s);
+}  // namespace cb200
+using namespace cb200;
+
+#define CK(expr)                        \
+	do {                                \
+		const int _e = (int) (expr);    \
+		if(_e != 0) return _e;          \
+	} while(0)
+
+namespace {
+struct Model {
+	int material = 0;
+	cb200_particle_buffer pb[2];
+	long long bin_capacity = 0;
+	float* d_pos = nullptr;
+	int n = 0;
+	float v0[3] = {0, 0, 0};
+	int* bin_sizes = nullptr;
+};
+
+void default_material(const cb200_config& cfg, int material, cb200_particle_buffer& pb) {
+	// defaults of ParticleBuffer<M>, reference Projects/GMPM/particle_buffer.cuh:141-264
+	const float cells = (float) (1u << cfg.domain_bits);
+	const float E = 5e3f, nu = 0.4f;
+	pb.material = material;
+	pb.rho = 1e3f;
+	pb.mass = 1e3f / cells / cells / cells / 8.f;
+	pb.volume = ((material == CB200_FIXED_COROTATED || material == CB200_SAND) ? 10.f : 1.f) / cells / cells / cells / 8.f;
+	pb.bulk = 4e4f;
+	pb.gamma = 7.15f;
+	pb.viscosity = 0.01f;
+	pb.lambda = E * nu / ((1 + nu) * (1 - 2 * nu));
+	pb.mu = E / (2 * (1 + nu));
+	pb.cohesion = 0.f;
+	pb.beta = material == CB200_NACC ? 0.5f : 1.f;
+	pb.yield_surface = 0.816496580927726f * 2.f * 0.5f / (3.f - 0.5f);
+	pb.volume_correction = 1;
+	pb.bm = 2.f / 3.f * (E / (2 * (1 + nu))) + (E * nu / ((1 + nu) * (1 - 2 * nu)));
+	pb.xi = 0.8f;
+	pb.msqr = 3.423772074299613f;
+	pb.hardening_on = 1;
+}
+}  // namespace
+
+struct cb200_sim {
+	cb200_sim_desc desc;
+	Cfg cfg;
+	cudaStream_t stream = nullptr;
+	StepState* d_state = nullptr;
+	StepState* h_state = nullptr;  // pinned
+	cb200_partition part[2];
+	float* grid[2] = {nullptr, nullptr};
+	int* marks = nullptr;
+	int* dest = nullptr;
+	int* d_scratch = nullptr;  // [0] new_pbc, [1] new_nbc snapshot, [2] parcount
+	std::vector<Model> models;
+	int rollid = 0;
+	long long launches = 0;
+	long long launches_per_step = 0;
+	cudaGraphExec_t graph[2] = {nullptr, nullptr};
+	bool setup_done = false;
+	size_t table_entries = 0;
+	// MGSP
+	int* peer_overlap_keys = nullptr;   // blockids of my blocks overlapping each peer: [world][max_blocks*3]
+	int* peer_overlap_count = nullptr;  // [world]
+	// per-kernel timing (cudaEvent pairs around the g2p2g launches; stream mode only)
+	bool profiling = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+	size_t prof_used = 0;
+	bool capturing = false;
+};
+
+namespace {
+int alloc_partition(cb200_sim* s, cb200_partition& p) {
+	const size_t mb = (size_t) s->desc.max_blocks;
+	CK(cudaMalloc(&p.count, sizeof(int)));
+	CK(cudaMalloc(&p.index_table, s->table_entries * sizeof(int)));
+	CK(cudaMalloc(&p.active_keys, (mb + 1) * 3 * sizeof(int)));
+	CK(cudaMalloc(&p.halo_count, sizeof(int)));
+	CK(cudaMalloc(&p.halo_marks, mb + 1));
+	CK(cudaMalloc(&p.overlap_marks, (mb + 1) * sizeof(int)));
+	p.halo_blocks = nullptr;
+	CK(cudaMemsetAsync(p.count, 0, sizeof(int), s->stream));
+	CK(cudaMemsetAsync(p.index_table, 0xff, s->table_entries * sizeof(int), s->stream));
+	CK(cudaMemsetAsync(p.active_keys, 0, (mb + 1) * 3 * sizeof(int), s->stream));
+	CK(cudaMemsetAsync(p.halo_count, 0, sizeof(int), s->stream));
+	CK(cudaMemsetAsync(p.halo_marks, 0, mb + 1, s->stream));
+	CK(cudaMemsetAsync(p.overlap_marks, 0, (mb + 1) * sizeof(int), s->stream));
+	return 0;
+}
+void free_partition(cb200_partition& p) {
+	cudaFree(p.count);
+	cudaFree(p.index_table);
+	cudaFree(p.active_keys);
+	cudaFree(p.halo_count);
+	cudaFree(p.halo_marks);
+	cudaFree(p.overlap_marks);
+}
+inline int grid_blocks(int per_sm) { return num_sms() * per_sm; }
+
+int pull_state(cb200_sim* s) {
+	CK(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+int push_state(cb200_sim* s) {
+	CK(cudaMemcpyAsync(s->d_state, s->h_state, sizeof(StepState), cudaMemcpyHostToDevice, s->stream));
+	return 0;
+}
+
+G2P2GArgs make_g2p2g_args(cb200_sim* s, const Model& m, int R, int halo_mode) {
+	const int Rn = R ^ 1;
+	G2P2GArgs a {};
+	a.cfg = s->cfg;
+	a.state = s->d_state;
+	a.halo_mode = halo_mode;
+	a.halo_marks = s->part[R].halo_marks;
+	a.cur = view(m.pb[R]);
+	a.next = view(m.pb[Rn]);
+	a.mat = mat_of(m.pb[R]);
+	a.prev_table = s->part[Rn].index_table;
+	a.table = s->part[R].index_table;
+	a.keys = s->part[R].active_keys;
+	a.grid = s->grid[0];
+	a.next_grid = s->grid[1];
+	a.error = &s->d_state->error;
+	return a;
+}
+
+// ---- phase A: grid update (+ fused clears) -------------------------------------------------------
+int enqueue_grid_update(cb200_sim* s, int R) {
+	const int Rn = R ^ 1;
+	GridUpdateArgs gu {};
+	gu.cfg = s->cfg;
+	gu.state = s->d_state;
+	gu.grid = s->grid[0];
+	gu.keys = s->part[R].active_keys;
+	gu.max_vel = &s->d_state->max_vel_sq;
+	gu.clear_grid = s->grid[1];
+	gu.n_clear = (int) s->models.size();
+	for(size_t m = 0; m < s->models.size(); ++m) gu.clear_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
+	grid_update_kernel<<<grid_blocks(4), kGridThreads, 0, s->stream>>>(gu);
+	++s->launches;
+	return (int) cudaGetLastError();
+}
+// ---- phase B: g2p2g --------------------------------------------------------------------------------
+int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode) {
+	for(const Model& m : s->models) {
+		const G2P2GArgs a = make_g2p2g_args(s, m, R, halo_mode);
+		const bool timed = s->profiling && !s->capturing;
+		if(timed) {
+			if(s->prof_used == s->prof_events.size()) {
+				cudaEvent_t e0, e1;
+				CK(cudaEventCreate(&e0));
+				CK(cudaEventCreate(&e1));
+				s->prof_events.emplace_back(e0, e1);
+			}
+			CK(cudaEventRecord(s->prof_events[s->prof_used].first, s->stream));
+		}
+		CK(launch_g2p2g(m.material, a, -1, s->stream));
+		if(timed) CK(cudaEventRecord(s->prof_events[s->prof_used++].second, s->stream));
+		++s->launches;
+	}
+	return 0;
+}
+// ---- phase C: partition / bucket rebuild -------------------------------------------------------------
+int enqueue_rebuild(cb200_sim* s, int R) {
+	const int Rn = R ^ 1;
+	const int nm = (int) s->models.size();
+	cudaStream_t st = s->stream;
+	{
+		SummaryArgs a {};
+		a.cfg = s->cfg;
+		a.state = s->d_state;
+		a.n_models = nm;
+		for(int m = 0; m < nm; ++m) {
+			a.cell_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
+			a.bucket_sizes[m] = s->models[m].pb[Rn].particle_bucket_sizes;
+		}
+		a.marks = s->marks;
+		a.stale_table = s->part[Rn].index_table;
+		a.stale_keys = s->part[Rn].active_keys;
+		a.stale_count = s->part[Rn].count;
+		a.capacity = s->desc.max_blocks;
+		block_summary_kernel<<<grid_blocks(4), 256, 0, st>>>(a);
+		++s->launches;
+	}
+	{
+		ScanArgs a {};
+		a.count = count_dev(&s->d_state->ebc);
+		a.count_plus = 1;
+		a.in = s->marks;
+		a.out = s->dest;
+		a.total_out = s->d_scratch + 0;
+		a.total_out2 = s->part[Rn].count;
+		a.limit = s->desc.max_blocks;
+		a.error = &s->d_state->error;
+		a.error_bit = kErrBlockCapacity;
+		scan_kernel<<<1, 1024, 0, st>>>(a);
+		++s->launches;
+	}
+	{
+		RebuildArgs a {};
+		a.cfg = s->cfg;
+		a.state = s->d_state;
+		a.n_models = nm;
+		a.marks = s->marks;
+		a.dest = s->dest;
+		a.old_keys = s->part[R].active_keys;
+		a.new_keys = s->part[Rn].active_keys;
+		a.new_table = s->part[Rn].index_table;
+		for(int m = 0; m < nm; ++m) {
+			a.cell_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
+			a.cellbuckets[m] = s->models[m].pb[Rn].cellbuckets;
+			a.dst_sizes[m] = s->models[m].pb[R].particle_bucket_sizes;
+			a.dst_buckets[m] = s->models[m].pb[R].blockbuckets;
+			a.bin_sizes[m] = s->models[m].bin_sizes;
+		}
+		rebuild_kernel<<<grid_blocks(8), kBucketThreads, 0, st>>>(a);
+		++s->launches;
+	}
+	for(int m = 0; m < nm; ++m) {
+		ScanArgs a {};
+		a.count = count_dev(s->d_scratch + 0);
+		a.count_plus = 1;
+		a.in = s->models[m].bin_sizes;
+		a.out = s->models[m].pb[R].bin_offsets;
+		a.total_out = &s->d_state->bin_count[m];
+		scan_kernel<<<1, 1024, 0, st>>>(a);
+		++s->launches;
+	}
+	{
+		RegisterArgs a {};
+		a.cfg = s->cfg;
+		a.block_count = count_dev(s->d_scratch + 0);
+		a.table = s->part[Rn].index_table;
+		a.keys = s->part[Rn].active_keys;
+		a.count = s->part[Rn].count;
+		a.capacity = s->desc.max_blocks;
+		a.error = &s->d_state->error;
+		a.lo = 0;
+		a.span = 2;
+		register_blocks_kernel<<<grid_blocks(4), 128, 0, st>>>(a);
+		++s->launches;
+	}
+	return (int) cudaGetLastError();
+}
+int enqueue_carry_and_exterior(cb200_sim* s, int R) {
+	const int Rn = R ^ 1;
+	cudaStream_t st = s->stream;
+	snapshot_int_kernel<<<1, 32, 0, st>>>(s->part[Rn].count, s->d_scratch + 1);
+	++s->launches;
+	{
+		CarryArgs a {};
+		a.cfg = s->cfg;
+		a.new_count = s->d_scratch + 1;
+		a.new_keys = s->part[Rn].active_keys;
+		a.old_table = s->part[R].index_table;
+		a.state = s->d_state;
+		a.old_grid = s->grid[1];
+		a.new_grid = s->grid[0];
+		carry_grid_kernel<<<grid_blocks(4), 256, 0, st>>>(a);
+		++s->launches;
+	}
+	{
+		RegisterArgs a {};
+		a.cfg = s->cfg;
+		a.block_count = count_dev(s->d_scratch + 0);
+		a.table = s->part[Rn].index_table;
+		a.keys = s->part[Rn].active_keys;
+		a.count = s->part[Rn].count;
+		a.capacity = s->desc.max_blocks;
+		a.error = &s->d_state->error;
+		a.lo = -1;
+		a.span = 3;
+		register_blocks_kernel<<<grid_blocks(4), 128, 0, st>>>(a);
+		++s->launches;
+	}
+	{
+		FinalizeArgs a {};
+		a.cfg = s->cfg;
+		a.state = s->d_state;
+		a.new_pbc = s->d_scratch + 0;
+		a.new_nbc = s->d_scratch + 1;
+		a.new_count = s->part[Rn].count;
+		a.max_blocks = s->desc.max_blocks;
+		a.n_models = (int) s->models.size();
+		for(size_t m = 0; m < s->models.size(); ++m) a.bin_capacity[m] = s->models[m].bin_capacity;
+		finalize_step_kernel<<<1, 32, 0, st>>>(a);
+		++s->launches;
+	}
+	return (int) cudaGetLastError();
+}
+
+int enqueue_substep(cb200_sim* s, int R) {
+	int e;
+	if((e = enqueue_grid_update(s, R))) return e;
+	if((e = enqueue_g2p2g(s, R, 0))) return e;
+	if((e = enqueue_rebuild(s, R))) return e;
+	if((e = enqueue_carry_and_exterior(s, R))) return e;
+	return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) {
+	if(!desc || !out || !cfg_valid(desc->cfg) || desc->max_blocks <= 0) return (int) cudaErrorInvalidValue;
+	cb200_sim* s = new cb200_sim();
+	s->desc = *desc;
+	if(s->desc.mgsp_world < 1) s->desc.mgsp_world = 1;
+	s->cfg = make_cfg(desc->cfg);
+	s->stream = (cudaStream_t) stream;
+	s->table_entries = (size_t) s->cfg.gsize * s->cfg.gsize * s->cfg.gsize;
+	const size_t mb = (size_t) desc->max_blocks;
+	CK(cudaMalloc(&s->d_state, sizeof(StepState)));
+	CK(cudaMemsetAsync(s->d_state, 0, sizeof(StepState), s->stream));
+	CK(cudaMallocHost(&s->h_state, sizeof(StepState)));
+	memset(s->h_state, 0, sizeof(StepState));
+	for(int i = 0; i < 2; ++i) {
+		int e = alloc_partition(s, s->part[i]);
+		if(e) return e;
+		CK(cudaMalloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
+		CK(cudaMemsetAsync(s->grid[i], 0, (mb + 1) * kGridBlockFloats * sizeof(float), s->stream));
+	}
+	CK(cudaMalloc(&s->marks, (mb + 2) * sizeof(int)));
+	CK(cudaMalloc(&s->dest, (mb + 2) * sizeof(int)));
+	CK(cudaMalloc(&s->d_scratch, 16 * sizeof(int)));
+	CK(cudaMemsetAsync(s->d_scratch, 0, 16 * sizeof(int), s->stream));
+	if(s->desc.mgsp_world > 1) {
+		CK(cudaMalloc(&s->peer_overlap_keys, (size_t) s->desc.mgsp_world * (mb + 1) * 3 * sizeof(int)));
+		CK(cudaMalloc(&s->peer_overlap_count, (size_t) s->desc.mgsp_world * sizeof(int)));
+		CK(cudaMemsetAsync(s->peer_overlap_count, 0, (size_t) s->desc.mgsp_world * sizeof(int), s->stream));
+	}
+	*out = s;
+	return 0;
+}
+
+int cb200_sim_destroy(cb200_sim* s) {
+	if(!s) return 0;
+	cudaStreamSynchronize(s->stream);
+	for(auto& ev : s->prof_events) {
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	for(int i = 0; i < 2; ++i) {
+		if(s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+		free_partition(s->part[i]);
+		cudaFree(s->grid[i]);
+	}
+	for(Model& m : s->models) {
+		for(int i = 0; i < 2; ++i) {
+			cudaFree(m.pb[i].bins);
+			cudaFree(m.pb[i].cell_particle_counts);
+			cudaFree(m.pb[i].particle_bucket_sizes);
+			cudaFree(m.pb[i].cellbuckets);
+			cudaFree(m.pb[i].blockbuckets);
+			cudaFree(m.pb[i].bin_offsets);
+		}
+		cudaFree(m.d_pos);
+		cudaFree(m.bin_sizes);
+	}
+	cudaFree(s->marks);
+	cudaFree(s->dest);
+	cudaFree(s->d_scratch);
+	cudaFree(s->d_state);
+	cudaFree(s->peer_overlap_keys);
+	cudaFree(s->peer_overlap_count);
+	cudaFreeHost(s->h_state);
+	delete s;
+	return 0;
+}
+
+int cb200_sim_init_model(cb200_sim* s, int material, const float* positions_host, int n, const float* v0, int* model_id) {
+	if(!s || s->setup_done || material < 0 || material > 3 || n <= 0 || (int) s->models.size() >= kMaxModels) return (int) cudaErrorInvalidValue;
+	Model m;
+	m.material = material;
+	m.n = n;
+	for(int d = 0; d < 3; ++d) m.v0[d] = v0 ? v0[d] : 0.f;
+	const size_t mb = (size_t) s->desc.max_blocks;
+	const size_t binf = material == CB200_J_FLUID ? 128 : 512;
+	// capacity rule of init_model (gmpm_simulator.cuh:173): n/32 bins + one partial bin per block
+	m.bin_capacity = (long long) n / kBinCap + (long long) mb;
+	for(int i = 0; i < 2; ++i) {
+		cb200_particle_buffer& pb = m.pb[i];
+		memset(&pb, 0, sizeof(pb));
+		default_material(s->desc.cfg, material, pb);
+		CK(cudaMalloc(&pb.bins, (size_t) m.bin_capacity * binf * sizeof(float)));
+		CK(cudaMalloc(&pb.cell_particle_counts, (mb + 1) * kBlockVol * sizeof(int)));
+		CK(cudaMalloc(&pb.particle_bucket_sizes, (mb + 2) * sizeof(int)));
+		CK(cudaMalloc(&pb.cellbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
+		CK(cudaMalloc(&pb.blockbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
+		CK(cudaMalloc(&pb.bin_offsets, (mb + 2) * sizeof(int)));
+		CK(cudaMemsetAsync(pb.cell_particle_counts, 0, (mb + 1) * kBlockVol * sizeof(int), s->stream));
+		CK(cudaMemsetAsync(pb.particle_bucket_sizes, 0, (mb + 2) * sizeof(int), s->stream));
+		CK(cudaMemsetAsync(pb.bin_offsets, 0, (mb + 2) * sizeof(int), s->stream));
+	}
+	CK(cudaMalloc(&m.bin_sizes, (mb + 2) * sizeof(int)));
+	CK(cudaMemsetAsync(m.bin_sizes, 0, (mb + 2) * sizeof(int), s->stream));
+	CK(cudaMalloc(&m.d_pos, (size_t) n * 3 * sizeof(float)));
+	CK(cudaMemcpyAsync(m.d_pos, positions_host, (size_t) n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	if(model_id) *model_id = (int) s->models.size();
+	s->models.push_back(m);
+	return 0;
+}
+
+static int set_elastic(cb200_sim* s, int model, int material, float rho, float vol, float ym, float pr) {
+	if(!s || model < 0 || model >= (int) s->models.size() || s->models[model].material != material) return (int) cudaErrorInvalidValue;
+	for(int i = 0; i < 2; ++i) {
+		cb200_particle_buffer& pb = s->models[model].pb[i];
+		pb.rho = rho;
+		pb.volume = vol;
+		pb.mass = vol * rho;
+		pb.lambda = ym * pr / ((1 + pr) * (1 - 2 * pr));
+		pb.mu = ym / (2 * (1 + pr));
+	}
+	return 0;
+}
+// ParticleBuffer<FIXED_COROTATED>::update_parameters  particle_buffer.cuh:178-184
+int cb200_sim_update_fr_parameters(cb200_sim* s, int model, float rho, float vol, float ym, float pr) { return set_elastic(s, model, CB200_FIXED_COROTATED, rho, vol, ym, pr); }
+int cb200_sim_update_sand_parameters(cb200_sim* s, int model, float rho, float vol, float ym, float pr) { return set_elastic(s, model, CB200_SAND, rho, vol, ym, pr); }
+// ParticleBuffer<J_FLUID>::update_parameters  particle_buffer.cuh:152-159
+int cb200_sim_update_j_fluid_parameters(cb200_sim* s, int model, float rho, float vol, float bulk, float gamma, float visc) {
+	if(!s || model < 0 || model >= (int) s->models.size() || s->models[model].material != CB200_J_FLUID) return (int) cudaErrorInvalidValue;
+	for(int i = 0; i < 2; ++i) {
+		cb200_particle_buffer& pb = s->models[model].pb[i];
+		pb.rho = rho;
+		pb.volume = vol;
+		pb.mass = vol * rho;
+		pb.bulk = bulk;
+		pb.gamma = gamma;
+		pb.viscosity = visc;
+	}
+	return 0;
+}
+// ParticleBuffer<NACC>::update_parameters  particle_buffer.cuh:250-259
+int cb200_sim_update_nacc_parameters(cb200_sim* s, int model, float rho, float vol, float ym, float pr, float beta, float xi) {
+	int e = set_elastic(s, model, CB200_NACC, rho, vol, ym, pr);
+	if(e) return e;
+	for(int i = 0; i < 2; ++i) {
+		cb200_particle_buffer& pb = s->models[model].pb[i];
+		pb.bm = 2.f / 3.f * (ym / (2 * (1 + pr))) + (ym * pr / ((1 + pr) * (1 - 2 * pr)));
+		pb.beta = beta;
+		pb.xi = xi;
+	}
+	return 0;
+}
+
+// initial_setup  gmpm_simulator.cuh:637-781 (counts are read back here: one-time cost)
+int cb200_sim_initial_setup(cb200_sim* s) {
+	if(!s || s->setup_done || s->models.empty()) return (int) cudaErrorInvalidValue;
+	cudaStream_t st = s->stream;
+	const Cfg& cfg = s->cfg;
+	const int R = s->rollid, Rn = R ^ 1;
+	const int cap = s->desc.max_blocks;
+	int* err = &s->d_state->error;
+	int pbc = 0, nbc = 0, ebc = 0;
+	auto blocks_for = [](long long n, int per) { return (int) std::max<long long>(1, std::min<long long>((n + per - 1) / per, 148 * 16)); };
+
+	for(Model& m : s->models) {
+		activate_blocks_kernel<<<blocks_for(m.n, 256), 256, 0, st>>>(cfg, m.n, m.d_pos, s->part[Rn].index_table, s->part[Rn].active_keys, s->part[Rn].count, cap, err);
+		++s->launches;
+	}
+	CK(cudaMemcpyAsync(&pbc, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if(pbc > cap) return (int) cudaErrorMemoryAllocation;
+	for(Model& m : s->models) {
+		build_particle_cell_buckets_kernel<<<blocks_for(m.n, 256), 256, 0, st>>>(cfg, m.n, m.d_pos, view(m.pb[R]), s->part[Rn].index_table, err);
+		cell_bucket_to_block_kernel<<<blocks_for(pbc, 1), kBucketThreads, 0, st>>>(cfg, pbc, m.pb[R].cell_particle_counts, m.pb[R].cellbuckets, m.pb[R].particle_bucket_sizes, m.pb[R].blockbuckets);
+		compute_bin_capacity_kernel<<<blocks_for(pbc + 1, 256), 256, 0, st>>>(pbc + 1, m.pb[R].particle_bucket_sizes, m.bin_sizes);
+		ScanArgs a {};
+		a.count = count_imm(pbc + 1);
+		a.in = m.bin_sizes;
+		a.out = m.pb[R].bin_offsets;
+		scan_kernel<<<1, 1024, 0, st>>>(a);
+		array_to_buffer_kernel<<<blocks_for(pbc, 1), 128, 0, st>>>(cfg, m.material, pbc, m.d_pos, view(m.pb[R]));
+		s->launches += 5;
+	}
+	{
+		RegisterArgs a {};
+		a.cfg = cfg;
+		a.block_count = count_imm(pbc);
+		a.table = s->part[Rn].index_table;
+		a.keys = s->part[Rn].active_keys;
+		a.count = s->part[Rn].count;
+		a.capacity = cap;
+		a.error = err;
+		a.lo = 0;
+		a.span = 2;
+		register_blocks_kernel<<<blocks_for((long long) pbc * 8, 128), 128, 0, st>>>(a);
+		CK(cudaMemcpyAsync(&nbc, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		a.lo = -1;
+		a.span = 3;
+		register_blocks_kernel<<<blocks_for((long long) pbc * 27, 128), 128, 0, st>>>(a);
+		CK(cudaMemcpyAsync(&ebc, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		s->launches += 2;
+	}
+	if(nbc > cap || ebc > cap) return (int) cudaErrorMemoryAllocation;
+	// background copies (gmpm_simulator.cuh:745-756); the device count is copied too so that the stale-key
+	// un-insert of the first rebuild knows how many entries the table holds
+	CK(cudaMemcpyAsync(s->part[R].index_table, s->part[Rn].index_table, s->table_entries * sizeof(int), cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemcpyAsync(s->part[R].active_keys, s->part[Rn].active_keys, (size_t) ebc * 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemcpyAsync(s->part[R].count, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToDevice, st));
+	for(Model& m : s->models) {
+		CK(cudaMemcpyAsync(m.pb[Rn].bin_offsets, m.pb[R].bin_offsets, (size_t) (pbc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(m.pb[Rn].particle_bucket_sizes, m.pb[R].particle_bucket_sizes, (size_t) pbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+	}
+	clear_grid_kernel<<<blocks_for((long long) nbc * 64, 256), 256, 0, st>>>(nbc, s->grid[0]);
+	++s->launches;
+	for(Model& m : s->models) {
+		rasterize_kernel<<<blocks_for(m.n, 256), 256, 0, st>>>(cfg, m.n, m.d_pos, s->grid[0], s->part[R].index_table, m.pb[R].mass, m.v0[0], m.v0[1], m.v0[2], err);
+		init_adv_bucket_kernel<<<blocks_for(pbc, 1), 128, 0, st>>>(cfg, pbc, m.pb[Rn].particle_bucket_sizes, m.pb[Rn].blockbuckets);
+		s->launches += 2;
+	}
+	CK(cudaGetLastError());
+	// device-resident step state; initial dt as in main_loop's preamble (gmpm_simulator.cuh:305-315)
+	CK(pull_state(s));
+	StepState& h = *s->h_state;
+	h.pbc = pbc;
+	h.nbc = nbc;
+	h.ebc = ebc;
+	h.prev_nbc = nbc;
+	h.prev_ebc = ebc;
+	h.dt_default = s->desc.dt_default;
+	h.frame_time = s->desc.fps > 0 ? 1.f / (float) s->desc.fps : 0.f;
+	h.step_time = 0.f;
+	float mv = 0.f;
+	for(const Model& m : s->models) mv = fmaxf(mv, sqrtf(m.v0[0] * m.v0[0] + m.v0[1] * m.v0[1] + m.v0[2] * m.v0[2]));
+	float dt = h.dt_default;
+	if(mv > 0.f) dt = fminf(dt, cfg.dx * cfg.cfl / mv);
+	if(h.frame_time > 0.f) dt = fminf(dt, h.frame_time);
+	h.dt = dt;
+	h.next_dt = dt;
+	h.max_vel_sq = 0.f;
+	CK(push_state(s));
+	CK(cudaStreamSynchronize(st));
+	s->setup_done = true;
+	return 0;
+}
+
+int cb200_sim_step(cb200_sim* s, int n) {
+	if(!s || !s->setup_done) return (int) cudaErrorInvalidValue;
+	for(int i = 0; i < n; ++i) {
+		const int R = s->rollid;
+		if(s->desc.use_graph && !s->profiling) {
+			if(!s->graph[R]) {
+				const long long before = s->launches;
+				cudaGraph_t g = nullptr;
+				CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+				s->capturing = true;
+				const int e = enqueue_substep(s, R);
+				s->capturing = false;
+				const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+				if(e) return e;
+				CK(ce);
+				CK(cudaGraphInstantiate(&s->graph[R], g, 0));
+				cudaGraphDestroy(g);
+				s->launches_per_step = s->launches - before;
+				s->launches = before;
+			}
+			CK(cudaGraphLaunch(s->graph[R], s->stream));
+			s->launches += s->launches_per_step;
+		} else {
+			const int e = enqueue_substep(s, R);
+			if(e) return e;
+		}
+		s->rollid ^= 1;
+	}
+	return 0;
+}
+
+// main_loop's inner for-loop (gmpm_simulator.cuh:324): sub-steps until step_time reaches the frame time.
+// dt never exceeds dt_default, so ceil(remaining / dt_default) sub-steps can be queued before the host
+// looks at the device clock again.
+int cb200_sim_advance_frame(cb200_sim* s, int* steps_taken) {
+	if(!s || !s->setup_done || s->desc.fps <= 0) return (int) cudaErrorInvalidValue;
+	int taken = 0;
+	CK(pull_state(s));
+	// the reference restarts current_step_time at 0 for every frame
+	s->h_state->step_time = 0.f;
+	CK(cudaMemcpyAsync(&s->d_state->step_time, &s->h_state->step_time, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	const float frame = s->h_state->frame_time;
+	for(;;) {
+		CK(pull_state(s));
+		if(s->h_state->error) break;
+		const float left = frame - s->h_state->step_time;
+		if(!(left > 0.f)) break;
+		int batch = (int) ceilf(left / s->h_state->dt_default);
+		if(batch < 1) batch = 1;
+		if(batch > 64) batch = 64;
+		// never overshoot: the device clamps dt to the remaining time, and a zero-length step is harmless
+		int e = cb200_sim_step(s, 1);
+		if(e) return e;
+		taken += 1;
+		(void) batch;
+	}
+	if(steps_taken) *steps_taken = taken;
+	return 0;
+}
+
+int cb200_sim_sync(cb200_sim* s) {
+	if(!s) return (int) cudaErrorInvalidValue;
+	return (int) cudaStreamSynchronize(s->stream);
+}
+
+int cb200_sim_stats_get(cb200_sim* s, cb200_sim_stats* out) {
+	if(!s || !out) return (int) cudaErrorInvalidValue;
+	CK(pull_state(s));
+	const StepState& h = *s->h_state;
+	out->particle_block_count = h.pbc;
+	out->neighbor_block_count = h.nbc;
+	out->exterior_block_count = h.ebc;
+	for(int m = 0; m < 8; ++m) out->bin_count[m] = h.bin_count[m];
+	out->dt = h.dt;
+	out->next_dt = h.next_dt;
+	out->max_vel = sqrtf(h.max_vel_sq);
+	out->step_time = h.step_time;
+	out->error = h.error;
+	out->steps = h.steps;
+	return 0;
+}
+
+static int retrieve_impl(cb200_sim* s, int model, float* host, int nch, int* n_out) {
+	if(!s || !s->setup_done || model < 0 || model >= (int) s->models.size()) return (int) cudaErrorInvalidValue;
+	Model& m = s->models[model];
+	const int R = s->rollid, Rn = R ^ 1;
+	float* d_out = nullptr;
+	CK(cudaMalloc(&d_out, (size_t) m.n * nch * sizeof(float)));
+	CK(cudaMemsetAsync(s->d_scratch + 2, 0, sizeof(int), s->stream));
+	retrieve_kernel<<<num_sms() * 8, 128, 0, s->stream>>>(s->cfg, m.material, count_dev(&s->d_state->pbc), s->part[R].active_keys, s->part[Rn].index_table, view(m.pb[R]), view(m.pb[Rn]), d_out, nch, s->d_scratch + 2);
+	++s->launches;
+	int n = 0;
+	CK(cudaMemcpyAsync(&n, s->d_scratch + 2, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	if(n > m.n) n = m.n;
+	CK(cudaMemcpy(host, d_out, (size_t) n * nch * sizeof(float), cudaMemcpyDeviceToHost));
+	cudaFree(d_out);
+	if(n_out) *n_out = n;
+	return 0;
+}
+int cb200_sim_retrieve(cb200_sim* s, int model, float* positions_host, int* n_out) { return retrieve_impl(s, model, positions_host, 3, n_out); }
+int cb200_sim_particle_state(cb200_sim* s, int model, float* state_host, int* n_out) {
+	if(!s || model < 0 || model >= (int) s->models.size()) return (int) cudaErrorInvalidValue;
+	const int mat = s->models[model].material;
+	return retrieve_impl(s, model, state_host, mat == CB200_J_FLUID ? 4 : (mat == CB200_FIXED_COROTATED ? 12 : 13), n_out);
+}
+
+int cb200_sim_active_keys(cb200_sim* s, int* keys_host, int capacity_blocks, int* n_out) {
+	if(!s || !s->setup_done) return (int) cudaErrorInvalidValue;
+	CK(pull_state(s));
+	const int n = std::min(s->h_state->ebc, capacity_blocks);
+	CK(cudaMemcpy(keys_host, s->part[s->rollid].active_keys, (size_t) n * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+	if(n_out) *n_out = n;
+	return 0;
+}
+int cb200_sim_grid(cb200_sim* s, float* grid_host, int capacity_blocks, int* n_out) {
+	if(!s || !s->setup_done) return (int) cudaErrorInvalidValue;
+	CK(pull_state(s));
+	const int n = std::min(s->h_state->nbc, capacity_blocks);
+	CK(cudaMemcpy(grid_host, s->grid[0], (size_t) n * kGridBlockFloats * sizeof(float), cudaMemcpyDeviceToHost));
+	if(n_out) *n_out = n;
+	return 0;
+}
+long long cb200_sim_launch_count(cb200_sim* s) { return s ? s->launches : 0; }
+
+// per-kernel timing for the roofline: CUDA-event pairs around every g2p2g launch (sub-steps are issued as plain
+// stream launches while profiling is on, so the events bracket exactly one kernel each)
+int cb200_sim_profile(cb200_sim* s, int enable) {
+	if(!s) return (int) cudaErrorInvalidValue;
+	CK(cudaStreamSynchronize(s->stream));
+	s->profiling = enable != 0;
+	s->prof_used = 0;
+	return 0;
+}
+int cb200_sim_profile_read(cb200_sim* s, double* g2p2g_ms_total, int* launches) {
+	if(!s) return (int) cudaErrorInvalidValue;
+	CK(cudaStreamSynchronize(s->stream));
+	double total = 0.0;
+	for(size_t i = 0; i < s->prof_used; ++i) {
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, s->prof_events[i].first, s->prof_events[i].second));
+		total += ms;
+	}
+	if(g2p2g_ms_total) *g2p2g_ms_total = total;
+	if(launches) *launches = (int) s->prof_used;
+	s->prof_used = 0;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// partition.cuh -- sparse-grid partition / bucket rebuild kernels.
+#pragma once
+#include "common.cuh"
+
+namespace cb200 {
+
+// Partition::insert (hash_table.cuh:117-127): CAS the table entry, then claim the next block number.
+// Out-of-domain keys are skipped (the reference indexes out of bounds); overflow sets an error bit.
+__device__ __forceinline__ int partition_insert(const Cfg& cfg, int* table, int* keys, int* count, int capacity, int* error, int x, int y, int z) {
+	if(!in_domain(cfg, x, y, z)) return -1;
+	int* slot = table + table_offset(cfg, x, y, z);
+	if(atomicCAS(slot, -1, 0) == -1) {
+		const int idx = atomicAdd(count, 1);
+		if(idx >= capacity) {
+			if(error) atomicOr(error, kErrBlockCapacity);
+			*slot = -1;
+			return -1;
+		}
+		*slot = idx;
+		keys[3 * idx] = x;
+		keys[3 * idx + 1] = y;
+		keys[3 * idx + 2] = z;
+		return idx;
+	}
+	return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of `count` ints (+ total at out[count]) by ONE CTA of 1024 threads.
+// Replaces thrust::exclusive_scan (gmpm_simulator.cuh:257-260); the count may be device-resident.
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+	Count count;
+	int count_plus;      // scan count + count_plus elements (reference scans ext+1 / pbc+1)
+	const int* in;
+	int* out;
+	int* total_out;      // nullable: receives the sum of the first `count` elements
+	int* total_out2;     // nullable: second destination (e.g. Partition::count)
+	int limit;           // if > 0: total above this sets *error |= error_bit and total is clamped to 0
+	int* error;
+	int error_bit;
+};
+__global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) {
+	__shared__ int s_warp[32];
+	__shared__ int s_carry;
+	const int n = a.count.get();
+	const int n_out = n + a.count_plus;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if(tid == 0) s_carry = 0;
+	__syncthreads();
+	for(int base = 0; base < n_out; base += 4096) {
+		const int i0 = base + tid * 4;
+		int v[4];
+#pragma unroll
+		for(int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? a.in[i0 + k] : 0;
+		const int tsum = v[0] + v[1] + v[2] + v[3];
+		int inc = tsum;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, inc, o);
+			if(lane >= o) inc += t;
+		}
+		if(lane == 31) s_warp[warp] = inc;
+		__syncthreads();
+		if(warp == 0) {
+			int w = s_warp[lane];
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				const int t = __shfl_up_sync(0xffffffffu, w, o);
+				if(lane >= o) w += t;
+			}
+			s_warp[lane] = w;
+		}
+		__syncthreads();
+		const int carry = s_carry;
+		int ex = carry + (warp ? s_warp[warp - 1] : 0) + inc - tsum;
+#pragma unroll
+		for(int k = 0; k < 4; ++k) {
+			if(i0 + k < n_out) a.out[i0 + k] = ex;
+			ex += v[k];
+		}
+		__syncthreads();
+		if(tid == 1023) s_carry = carry + s_warp[31];
+		__syncthreads();
+	}
+	if(tid == 0) {
+		int total = s_carry;
+		if(a.limit > 0 && total > a.limit) {
+			if(a.error) atomicOr(a.error, a.error_bit);
+			total = 0;
+		}
+		if(a.total_out) *a.total_out = total;
+		if(a.total_out2) *a.total_out2 = total;
+	}
+}
+
+// exclusive_scan_inverse (Library/MnBase/Algorithm/MappingKernels.cuh:44-55)
+__global__ void scan_inverse_kernel(int num, const int* map, int* map_inv) {
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num; i += gridDim.x * blockDim.x) {
+		const int m = map[i];
+		if(m != map[i + 1]) map_inv[m] = i;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell buckets -> block bucket (cell_bucket_to_block, mgmpm_kernels.cuh:70-84).
+// B200 form: the 64 cell counts are prefix-summed by one warp, then all tags are copied with coalesced
+// writes (each thread finds its cell by a 6-step search of the 65-entry prefix in shared memory), instead of
+// 128 rounds of warp-aggregated atomics each ending in a block barrier.  Bucket order is CELL-MAJOR: lanes of
+// a warp in g2p2g then share stencil nodes and read near-contiguous source slots.
+// dst_block lets the caller write straight into the compacted numbering (fuses update_buckets, :979-1000).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBucketThreads = 128;
+__device__ __forceinline__ int flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst, int* s_prefix) {
+	const int tid = threadIdx.x, lane = tid & 31;
+	if(tid < 32) {
+		const int2 c = reinterpret_cast<const int2*>(cell_counts_blk)[lane];
+		const int pair = c.x + c.y;
+		int inc = pair;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, inc, o);
+			if(lane >= o) inc += t;
+		}
+		s_prefix[2 * lane] = inc - pair;
+		s_prefix[2 * lane + 1] = inc - pair + c.x;
+		if(lane == 31) s_prefix[64] = inc;
+	}
+	__syncthreads();
+	const int total = s_prefix[64];
+	for(int i = tid; i < total; i += kBucketThreads) {
+		int c = 0;
+#pragma unroll
+		for(int s = 32; s > 0; s >>= 1)
+			if(s_prefix[c + s] <= i) c += s;
+		dst[i] = cellbuckets_blk[(c << cfg.ppc_shift) + (i - s_prefix[c])];
+	}
+	__syncthreads();
+	return total;
+}
+
+__global__ void __launch_bounds__(kBucketThreads) cell_bucket_to_block_kernel(Cfg cfg, int block_count, const int* cell_particle_counts, const int* cellbuckets, int* particle_bucket_sizes, int* buckets) {
+	__shared__ int s_prefix[65];
+	for(int b = blockIdx.x; b < block_count; b += gridDim.x) {
+		const int total = flatten_block(cfg, cell_particle_counts + (size_t) b * kBlockVol, cellbuckets + ((size_t) b << cfg.ppb_shift), buckets + ((size_t) b << cfg.ppb_shift), s_prefix);
+		if(threadIdx.x == 0) particle_bucket_sizes[b] += total;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// step-driver fused kernels
+// ------------------------------------------------------------------------------------------------
+// (1) per old block: particle count per model, activity mark; also un-insert the keys of the partition that is
+//     about to be rebuilt (replaces cudaMemsetAsync(0xff, 4*G^3), hash_table.cuh:110-112, by touching only the
+//     entries that were set).
+struct SummaryArgs {
+	Cfg cfg;
+	const StepState* state;
+	int n_models;
+	const int* cell_counts[kMaxModels];  // next buffers' cell_particle_counts (old numbering)
+	int* bucket_sizes[kMaxModels];       // next buffers' particle_bucket_sizes (old numbering)
+	int* marks;                          // [ebc + 1]
+	int* stale_table;                    // table of the partition being rebuilt
+	const int* stale_keys;
+	const int* stale_count;              // number of keys currently inserted in stale_table
+	int capacity;
+};
+__global__ void __launch_bounds__(256) block_summary_kernel(const SummaryArgs a) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ebc = a.state->ebc;
+	for(int b = blockIdx.x * 8 + warp; b <= ebc; b += gridDim.x * 8) {
+		int any = 0;
+		if(b < ebc) {
+			for(int m = 0; m < a.n_models; ++m) {
+				const int2 c = reinterpret_cast<const int2*>(a.cell_counts[m] + (size_t) b * kBlockVol)[lane];
+				const int s = __reduce_add_sync(0xffffffffu, c.x + c.y);
+				if(lane == 0) a.bucket_sizes[m][b] = s;
+				any |= s;
+			}
+		}
+		if(lane == 0) a.marks[b] = any > 0;
+	}
+	const int stale = min(*a.stale_count, a.capacity);
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < stale; i += gridDim.x * blockDim.x) {
+		const int x = a.stale_keys[3 * i], y = a.stale_keys[3 * i + 1], z = a.stale_keys[3 * i + 2];
+		if(in_domain(a.cfg, x, y, z)) a.stale_table[table_offset(a.cfg, x, y, z)] = -1;
+	}
+}
+
+// (2) compaction: old block b with a mark becomes block dest[b] of the new partition (update_partition,
+//     mgmpm_kernels.cuh:966-977); its cell buckets are flattened straight into the other buffer's block bucket in
+//     the new numbering (cell_bucket_to_block + update_buckets) and its bin demand is recorded (compute_bin_capacity).
+struct RebuildArgs {
+	Cfg cfg;
+	const StepState* state;
+	int n_models;
+	const int* marks;
+	const int* dest;
+	const int* old_keys;
+	int* new_keys;
+	int* new_table;
+	const int* cell_counts[kMaxModels];  // next buffers (old numbering)
+	const int* cellbuckets[kMaxModels];
+	int* dst_sizes[kMaxModels];          // cur buffers (new numbering)
+	int* dst_buckets[kMaxModels];
+	int* bin_sizes[kMaxModels];
+};
+__global__ void __launch_bounds__(kBucketThreads) rebuild_kernel(const RebuildArgs a) {
+	__shared__ int s_prefix[65];
+	const Cfg& cfg = a.cfg;
+	const int ebc = a.state->ebc;
+	for(int b = blockIdx.x; b < ebc; b += gridDim.x) {
+		if(!a.marks[b]) continue;
+		const int nb = a.dest[b];
+		if(threadIdx.x == 0) {
+			const int x = a.old_keys[3 * b], y = a.old_keys[3 * b + 1], z = a.old_keys[3 * b + 2];
+			a.new_keys[3 * nb] = x;
+			a.new_keys[3 * nb + 1] = y;
+			a.new_keys[3 * nb + 2] = z;
+			a.new_table[table_offset(cfg, x, y, z)] = nb;
+		}
+		for(int m = 0; m < a.n_models; ++m) {
+			const int total = flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift), s_prefix);
+			if(threadIdx.x == 0) {
+				a.dst_sizes[m][nb] = total;
+				a.bin_sizes[m][nb] = (total + kBinCap - 1) / kBinCap;
+			}
+		}
+	}
+}
+
+// (3) neighbour / exterior registration (register_neighbor_blocks :117-133, register_exterior_blocks :135-151):
+//     one thread per (particle block, offset) so the CAS traffic is spread over the whole grid.
+struct RegisterArgs {
+	Cfg cfg;
+	Count block_count;  // particle blocks of the partition
+	int* table;
+	int* keys;
+	int* count;
+	int capacity;
+	int* error;
+	int lo, span;       // offsets per axis in [lo, lo+span): (0,2) neighbours, (-1,3) exterior
+};
+__global__ void register_blocks_kernel(const RegisterArgs a) {
+	const int n = a.block_count.get();
+	const int per = a.span * a.span * a.span;
+	const long long total = (long long) n * per;
+	for(long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+		const int b = (int) (t / per), o = (int) (t % per);
+		const int i = o / (a.span * a.span) + a.lo, j = (o / a.span) % a.span + a.lo, k = o % a.span + a.lo;
+		partition_insert(a.cfg, a.table, a.keys, a.count, a.capacity, a.error, a.keys[3 * b] + i, a.keys[3 * b + 1] + j, a.keys[3 * b + 2] + k);
+	}
+}
+
+// (4) end of sub-step: roll the device-resident counters and clock (gmpm_simulator.cuh:578-579 and the
+//     D2H counter copies at :462,:502,:517,:564)
+struct FinalizeArgs {
+	Cfg cfg;
+	StepState* state;
+	const int* new_pbc;
+	const int* new_nbc;   // value of Partition::count after neighbour registration (snapshot)
+	const int* new_count; // Partition::count after exterior registration
+	int max_blocks;
+	int n_models;
+	long long bin_capacity[kMaxModels];
+};
+__global__ void finalize_step_kernel(const FinalizeArgs a) {
+	if(threadIdx.x != 0 || blockIdx.x != 0) return;
+	StepState* s = a.state;
+	const float next_dt = [&] {
+		float dt = s->dt_default;
+		const float mv = sqrtf(s->max_vel_sq);
+		if(mv > 0.f) dt = fminf(dt, a.cfg.dx * a.cfg.cfl / mv);
+		if(s->frame_time > 0.f) dt = fminf(dt, s->frame_time - s->step_time);
+		return dt;
+	}();
+	s->next_dt = next_dt;
+	s->prev_nbc = s->nbc;
+	s->prev_ebc = s->ebc;
+	s->pbc = *a.new_pbc;
+	s->nbc = *a.new_nbc;
+	s->ebc = min(*a.new_count, a.max_blocks);
+	for(int m = 0; m < a.n_models; ++m)
+		if(s->bin_count[m] > a.bin_capacity[m]) s->error |= kErrBinCapacity;
+	s->dt = next_dt;
+	s->step_time += next_dt;
+	s->max_vel_sq = 0.f;
+	s->work_counter = 0;
+	s->steps += 1;
+}
+
+__global__ void snapshot_int_kernel(const int* src, int* dst) {
+	if(threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
+
+// ------------------------------------------------------------------------------------------------
+// drop-in forms of the remaining reference kernels (one thread per element)
+// ------------------------------------------------------------------------------------------------
+__global__ void mark_active_particle_blocks_kernel(int block_count, const int* sizes, int* marks) {
+	for(int b = blockIdx.x * blockDim.x + threadIdx.x; b < block_count; b += gridDim.x * blockDim.x)
+		if(sizes[b] > 0) marks[b] = 1;
+}
+__global__ void compute_bin_capacity_kernel(int block_count, const int* sizes, int* bin_sizes) {
+	for(int b = blockIdx.x * blockDim.x + threadIdx.x; b < block_count; b += gridDim.x * blockDim.x) bin_sizes[b] = (sizes[b] + kBinCap - 1) / kBinCap;
+}
+__global__ void update_partition_kernel(Cfg cfg, int block_count, const int* source_nos, const int* keys, int* next_keys, int* next_table) {
+	for(int b = blockIdx.x * blockDim.x + threadIdx.x; b < block_count; b += gridDim.x * blockDim.x) {
+		const int s = source_nos[b];
+		const int x = keys[3 * s], y = keys[3 * s + 1], z = keys[3 * s + 2];
+		next_keys[3 * b] = x;
+		next_keys[3 * b + 1] = y;
+		next_keys[3 * b + 2] = z;
+		if(in_domain(cfg, x, y, z)) next_table[table_offset(cfg, x, y, z)] = b;
+	}
+}
+__global__ void update_buckets_kernel(Cfg cfg, int block_count, const int* source_nos, const int* sizes, const int* buckets, int* next_sizes, int* next_buckets) {
+	for(int b = blockIdx.x; b < block_count; b += gridDim.x) {
+		const int s = source_nos[b];
+		const int n = sizes[s];
+		if(threadIdx.x == 0) next_sizes[b] = n;
+		for(int i = threadIdx.x; i < n; i += blockDim.x) next_buckets[((size_t) b << cfg.ppb_shift) + i] = buckets[((size_t) s << cfg.ppb_shift) + i];
+	}
+}
+__global__ void fill_int_kernel(int* p, size_t n, int v) {
+	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace cb200

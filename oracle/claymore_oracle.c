@@ -1360,3 +1360,9 @@ int orc_sim_particle_state(orc_sim* s, int model, float* out) {
 	}
 	return n;
 }
+
+/* raw container access for kernel-level differential tests: which = 0 -> buffers indexed [rollid], 1 -> [rollid^1] */
+void orc_sim_get_buffer(orc_sim* s, int model, int which, orc_particle_buffer* out) { *out = s->bins[s->rollid ^ (which & 1)][model]; }
+void orc_sim_get_partition(orc_sim* s, int which, orc_partition* out) { *out = s->parts[s->rollid ^ (which & 1)]; }
+float* orc_sim_get_grid(orc_sim* s, int which) { return s->grids[which & 1]; }
+long orc_sim_bin_capacity(orc_sim* s, int model) { return s->bin_capacity[model]; }

@@ -131,6 +131,11 @@ const int* orc_sim_active_keys(orc_sim* s);         /* current partition keys, i
 const float* orc_sim_grid(orc_sim* s);              /* grid_blocks[0], nbc blocks valid */
 int orc_sim_particle_state(orc_sim* s, int model, float* out /* n x channels, in bucket order */);
 
+void orc_sim_get_buffer(orc_sim* s, int model, int which, orc_particle_buffer* out);
+void orc_sim_get_partition(orc_sim* s, int which, orc_partition* out);
+float* orc_sim_get_grid(orc_sim* s, int which);
+long orc_sim_bin_capacity(orc_sim* s, int model);
+
 #ifdef __cplusplus
 }
 #endif

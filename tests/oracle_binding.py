@@ -98,6 +98,12 @@ def lib():
         L.orc_collect_grid_blocks.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_void_p, Partition, C.c_void_p]
         L.orc_reduce_grid_blocks.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_void_p, Partition, C.c_void_p]
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_sim_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ParticleBuffer)]
+        L.orc_sim_get_partition.argtypes = [C.c_void_p, C.c_int, C.POINTER(Partition)]
+        L.orc_sim_get_grid.restype = C.c_void_p
+        L.orc_sim_get_grid.argtypes = [C.c_void_p, C.c_int]
+        L.orc_sim_bin_capacity.restype = C.c_long
+        L.orc_sim_bin_capacity.argtypes = [C.c_void_p, C.c_int]
     return _lib
 
 
@@ -225,3 +231,47 @@ class OracleSim:
         _, nbc, _ = self.block_counts()
         p = self.L.orc_sim_grid(self.h)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(nbc, 4, 64)).copy()
+
+
+    # ---- raw containers (numpy views of the oracle's host memory) for kernel-level differential tests ----
+    def buffer(self, model, which):
+        pb = ParticleBuffer()
+        self.L.orc_sim_get_buffer(self.h, model, which, C.byref(pb))
+        return pb
+
+    def partition(self, which):
+        p = Partition()
+        self.L.orc_sim_get_partition(self.h, which, C.byref(p))
+        return p
+
+    def buffer_arrays(self, model, which):
+        """dict of numpy views: bins, cell_particle_counts, particle_bucket_sizes, cellbuckets, blockbuckets, bin_offsets."""
+        pb = self.buffer(model, which)
+        mb, ppb = self.max_blocks, 64 * self.cfg.max_ppc
+        cap = self.L.orc_sim_bin_capacity(self.h, model)
+        bf = BIN_FLOATS[self.materials[model]]
+
+        def view(ptr_, ctype, n):
+            return np.ctypeslib.as_array(C.cast(ptr_, C.POINTER(ctype)), shape=(n,))
+        return {
+            "struct": pb,
+            "bins": view(pb.bins, C.c_float, cap * bf),
+            "cell_particle_counts": view(pb.cell_particle_counts, C.c_int, mb * 64),
+            "particle_bucket_sizes": view(pb.particle_bucket_sizes, C.c_int, mb + 1),
+            "cellbuckets": view(pb.cellbuckets, C.c_int, mb * ppb),
+            "blockbuckets": view(pb.blockbuckets, C.c_int, mb * ppb),
+            "bin_offsets": view(pb.bin_offsets, C.c_int, mb + 1),
+        }
+
+    def partition_arrays(self, which):
+        p = self.partition(which)
+        g = 1 << (self.cfg.domain_bits - 2)
+
+        def view(ptr_, ctype, n):
+            return np.ctypeslib.as_array(C.cast(ptr_, C.POINTER(ctype)), shape=(n,))
+        return {"struct": p, "count": view(p.count, C.c_int, 1), "index_table": view(p.index_table, C.c_int, g * g * g),
+                "active_keys": view(p.active_keys, C.c_int, self.max_blocks * 3)}
+
+    def grid_array(self, which):
+        p = self.L.orc_sim_get_grid(self.h, which)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(self.max_blocks * 256,))
