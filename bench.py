@@ -190,8 +190,10 @@ def run_b200(args):
     dx = 1.0 / (1 << scene["domain_bits"])
     mb = max_blocks_for(scene)
 
+    stream = torch.cuda.Stream()  # the kernels are launched on this stream; the timing events are recorded on it too
+
     def fresh(use_graph):
-        return scenes.build_engine(scene, dt=args.dt, max_blocks=mb, use_graph=use_graph)
+        return scenes.build_engine(scene, dt=args.dt, max_blocks=mb, use_graph=use_graph, stream=stream.cuda_stream)
 
     # ---- device-resident timing: K sub-steps, CUDA events, graph replay --------------------------------------
     sim = fresh(use_graph=not args.no_graph)
@@ -204,9 +206,9 @@ def run_b200(args):
     l0 = sim.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    e0.record()
+    e0.record(stream)
     sim.step(args.steps)
-    e1.record()
+    e1.record(stream)
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     launches = sim.launch_count - l0
@@ -247,7 +249,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     cfg = cb.Config(domain_bits=scene["domain_bits"])
-    sim2 = cb.GmpmSimulator(dt=args.dt, fps=0, config=cfg, max_blocks=mb, use_graph=not args.no_graph)
+    sim2 = cb.GmpmSimulator(dt=args.dt, fps=0, config=cfg, max_blocks=mb, use_graph=not args.no_graph, stream=stream.cuda_stream)
     for m, p in zip(scene["models"], pinned):
         mid = sim2.init_model(m["material"], p.numpy(), m["v0"])
         scenes.apply_material(sim2, mid, m["material"], dx, False)

@@ -93,6 +93,7 @@ struct cb200_sim {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 	size_t prof_used = 0;
 	bool capturing = false;
+	bool owns_stream = false;
 };
 
 namespace {
@@ -336,6 +337,10 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 	if(s->desc.mgsp_world < 1) s->desc.mgsp_world = 1;
 	s->cfg = make_cfg(desc->cfg);
 	s->stream = (cudaStream_t) stream;
+	if(!s->stream) {  // the legacy default stream cannot be captured into a graph: own a stream instead
+		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		s->owns_stream = true;
+	}
 	s->table_entries = (size_t) s->cfg.gsize * s->cfg.gsize * s->cfg.gsize;
 	const size_t mb = (size_t) desc->max_blocks;
 	CK(cudaMalloc(&s->d_state, sizeof(StepState)));
@@ -392,6 +397,7 @@ int cb200_sim_destroy(cb200_sim* s) {
 	cudaFree(s->peer_overlap_keys);
 	cudaFree(s->peer_overlap_count);
 	cudaFreeHost(s->h_state);
+	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return 0;
 }
