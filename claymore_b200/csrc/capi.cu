@@ -31,7 +31,8 @@ template<int MAT>
 static int g2p2g_blocks_per_sm() {
 	static int v = 0;
 	if(!v) {
-		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, g2p2g_kernel<MAT>, kG2P2GThreads, 0) != cudaSuccess || v <= 0) v = 4;
+		cudaFuncSetAttribute(g2p2g_kernel<MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(G2P2GSmem));
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, g2p2g_kernel<MAT>, kG2P2GThreads, sizeof(G2P2GSmem)) != cudaSuccess || v <= 0) v = 3;
 	}
 	return v;
 }
@@ -50,10 +51,10 @@ cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaS
 	if(block_hint >= 0 && block_hint < grid) grid = block_hint;
 	if(grid < 1) return cudaSuccess;
 	switch(material) {
-		case CB200_J_FLUID: g2p2g_kernel<CB200_J_FLUID><<<grid, kG2P2GThreads, 0, s>>>(a); break;
-		case CB200_FIXED_COROTATED: g2p2g_kernel<CB200_FIXED_COROTATED><<<grid, kG2P2GThreads, 0, s>>>(a); break;
-		case CB200_SAND: g2p2g_kernel<CB200_SAND><<<grid, kG2P2GThreads, 0, s>>>(a); break;
-		case CB200_NACC: g2p2g_kernel<CB200_NACC><<<grid, kG2P2GThreads, 0, s>>>(a); break;
+		case CB200_J_FLUID: g2p2g_kernel<CB200_J_FLUID><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
+		case CB200_FIXED_COROTATED: g2p2g_kernel<CB200_FIXED_COROTATED><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
+		case CB200_SAND: g2p2g_kernel<CB200_SAND><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
+		case CB200_NACC: g2p2g_kernel<CB200_NACC><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
 	}
 	return cudaGetLastError();
 }

@@ -1,24 +1,38 @@
 // g2p2g.cuh -- the fused grid-to-particle / constitutive update / particle-to-grid kernel for sm_100a.
 //
-// Replaces g2p2g<Partition<1>, GridBuffer, M> (reference Projects/GMPM/mgmpm_kernels.cuh:665-937,
-// with fetch_particle_buffer_data :428-462, calculate_contribution_and_store_particle_data :470-663 and
-// ParticleBufferImpl::add_advection particle_buffer.cuh:100-135).  Same inputs, same outputs, same
-// containers; different machine mapping:
-//   * one CTA walks particle blocks (persistent, grid-stride) instead of one CUDA block per particle block;
-//   * the 2x2x2 neighbourhood of grid blocks is staged into shared memory with eight 768-byte TMA bulk
-//     copies (the three velocity channels of a grid block are contiguous) signalled on an mbarrier,
-//     instead of 1536 scalar loads each preceded by a table query (:700-726);
-//   * P2G accumulates into a shared arena that has the grid-block layout, so the write-back is eight
-//     1-KiB cp.reduce.async.bulk f32-add operations executed by the TMA unit, not 2048 SM-issued global
-//     atomics (:910-936);
-//   * the 27 neighbour block numbers and source bin offsets are resolved once per block into shared
-//     memory instead of two dependent global loads per particle (:761-767, particle_buffer.cuh:101-102).
+// Replaces g2p2g<Partition<1>, GridBuffer, M> (reference Projects/GMPM/mgmpm_kernels.cuh:665-937, with
+// fetch_particle_buffer_data :428-462, calculate_contribution_and_store_particle_data :470-663 and
+// ParticleBufferImpl::add_advection particle_buffer.cuh:100-135).  Same inputs, same outputs, same containers;
+// different machine mapping:
+//   * one CTA of 192 threads walks particle blocks (persistent, grid-stride) instead of one 128-thread CUDA block
+//     per particle block;
+//   * the 2x2x2 neighbourhood of grid blocks is staged with eight 768-byte TMA bulk copies (the three velocity
+//     channels of a grid block are contiguous) signalled on an mbarrier, then transposed in shared memory to one
+//     float4 per node so that G2P issues 27 LDS.128 instead of 81 LDS.32 (reference: 1536 scalar global loads each
+//     preceded by a table query, :700-726);
+//   * P2G does NOT scatter per particle.  Shared-memory float atomicAdd is a compare-and-swap loop on this
+//     hardware (LDS, FADD, ATOMS.CAST.SPIN, BRA) and 108 of them per particle were 63 % of all instructions in the
+//     first version of this kernel (profiles/r01_v0_*).  Instead:
+//       phase 1  particle-parallel: gather, G2P, advection, F update, stress, bin store, re-bucketing; the P2G
+//                inputs of each particle (local position, q = m v - C x_p, D = C dx: 15 floats) are staged in
+//                shared memory and counting-sorted by cell with native integer shared atomics;
+//       phase 2  cell-parallel: thread (cell, i-slice) walks the particles of its cell and accumulates its 9 nodes x
+//                4 channels in registers, then adds them to the arena once per cell: 108 adds per CELL, not per
+//                particle, and never two lanes of one instruction on the same address;
+//       phase 3  the few particles that changed cell in this step are scattered node-parallel.
+//   * the arena has the grid-block layout, so the write-back is eight 1-KiB cp.reduce.async.bulk f32-add operations
+//     executed by the TMA unit, not 2048 SM-issued global atomics (:910-936);
+//   * the 27 neighbour block numbers and source bin offsets are resolved once per block into shared memory instead
+//     of two dependent global loads per particle (:761-767, particle_buffer.cuh:101-102).
+// The kernel makes no assumption on the order of a block bucket (the reference's order is atomics-dependent);
+// cell-major buckets (partition.cuh) merely make the gathers of phase 1 nearly contiguous.
 #pragma once
 #include "math3.cuh"
 
 namespace cb200 {
 
-constexpr int kG2P2GThreads = 128;
+constexpr int kG2P2GThreads = 192;  // 64 cells x 3 stencil slices in phase 2
+constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
 
 struct G2P2GArgs {
 	Cfg cfg;
@@ -46,26 +60,45 @@ __device__ __forceinline__ float device_compute_dt(const Cfg& cfg, float max_vel
 	return dt;
 }
 
-template<int S>
-__device__ __forceinline__ int arena_off_x(int X) { return ((X >> 2) << 2) * S + ((X & 3) << 4); }
-template<int S>
-__device__ __forceinline__ int arena_off_y(int Y) { return ((Y >> 2) << 1) * S + ((Y & 3) << 2); }
-template<int S>
-__device__ __forceinline__ int arena_off_z(int Z) { return (Z >> 2) * S + (Z & 3); }
+// accumulation arena: [block 2x2x2][channel 4][cell 4x4x4] floats == eight grid blocks back to back
+__device__ __forceinline__ int acc_off_x(int X) { return ((X >> 2) << 2) * 256 + ((X & 3) << 4); }
+__device__ __forceinline__ int acc_off_y(int Y) { return ((Y >> 2) << 1) * 256 + ((Y & 3) << 2); }
+__device__ __forceinline__ int acc_off_z(int Z) { return (Z >> 2) * 256 + (Z & 3); }
+
+struct G2P2GSmem {
+	float4 vel4[512];                // node-major velocity arena, index (X*8+Y)*8+Z
+	float acc[8 * 256];              // accumulation arena (grid-block layout)
+	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads
+	float velsoa[8 * 192];           // TMA landing zone: 8 blocks x 3 channels x 64 cells
+	unsigned short idx[kChunk];      // staged slots sorted by cell
+	unsigned short movers[kChunk];   // staged slots of particles that changed cell
+	int cnt[64];
+	int start[65];
+	int nbr[27];
+	int srcbin[27];
+	int nmovers;
+	unsigned long long bar;
+};
+
+constexpr int kRecMover = 1 << 30;
+constexpr int kRecDrop = 1 << 29;
+
+// quadratic B-spline weight of stencil node i as a polynomial in d = local position / dx in [0.5, 1.5)
+__device__ __forceinline__ void bspline_poly(int i, float& a, float& b, float& c) {
+	a = i == 0 ? 1.125f : (i == 1 ? -0.25f : 0.125f);
+	b = i == 0 ? -1.5f : (i == 1 ? 2.f : -0.5f);
+	c = i == 1 ? -1.f : 0.5f;
+}
 
 template<int MAT>
 __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a) {
-	constexpr int NCH = (MAT == CB200_J_FLUID) ? 4 : (MAT == CB200_FIXED_COROTATED ? 12 : 13);
 	constexpr int BINF = (MAT == CB200_J_FLUID) ? 128 : 512;
-	constexpr int VS = 192;  // floats per block in the velocity arena (3 channels)
-	constexpr int AS = 256;  // floats per block in the accumulation arena (4 channels)
-	(void) NCH;
+	constexpr int T = kG2P2GThreads;
+	constexpr int ITERS = (kChunk + T - 1) / T;
 
-	__shared__ __align__(128) float s_vel[8 * VS];
-	__shared__ __align__(128) float s_acc[8 * AS];
-	__shared__ int s_nbr[27];
-	__shared__ int s_srcbin[27];
-	__shared__ __align__(8) uint64_t s_bar;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	G2P2GSmem& sm = *reinterpret_cast<G2P2GSmem*>(smem_raw);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar);
 
 	const Cfg& cfg = a.cfg;
 	const int tid = threadIdx.x;
@@ -77,13 +110,16 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 		nblocks = a.state->pbc;
 	}
 	if(tid == 0) {
-		mbar_init(&s_bar, 1);
+		mbar_init(bar, 1);
 		mbar_fence_init();
+		sm.nmovers = 0;
 	}
+	if(tid < 64) sm.cnt[tid] = 0;
 	__syncthreads();
 	unsigned phase = 0;
 	const float dx = cfg.dx, dx_inv = cfg.dx_inv, d_inv = cfg.d_inv;
 	const int ppb_mask = cfg.ppb - 1;
+	const float mass = a.mat.mass;
 
 	for(int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
 		const int bucket_size = a.next.particle_bucket_sizes[blk];
@@ -99,210 +135,320 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 			const int lb = tid & 7;
 			const int bno = table_query(cfg, a.table, kx + ((lb >> 2) & 1), ky + ((lb >> 1) & 1), kz + (lb & 1));
 			const unsigned valid = __ballot_sync(0xffffffffu, tid < 8 && bno >= 0);
-			if(tid == 0) mbar_arrive_expect_tx(&s_bar, __popc(valid) * (VS * 4));
+			if(tid == 0) mbar_arrive_expect_tx(bar, __popc(valid) * 768);
 			__syncwarp();
 			if(tid < 8) {
 				if(bno >= 0) {
-					tma_load_1d(s_vel + lb * VS, a.grid + (size_t) bno * kGridBlockFloats + 64, VS * 4, &s_bar);
+					tma_load_1d(sm.velsoa + lb * 192, a.grid + (size_t) bno * kGridBlockFloats + 64, 768, bar);
 				} else {
-					for(int i = 0; i < VS; ++i) s_vel[lb * VS + i] = 0.f;
+					for(int i = 0; i < 192; ++i) sm.velsoa[lb * 192 + i] = 0.f;
 				}
 			}
 		} else if(tid < 32 + 27) {
 			const int d = tid - 32;
 			const int ox = d / 9 - 1, oy = (d / 3) % 3 - 1, oz = d % 3 - 1;
-			s_nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
+			sm.nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
 			const int pno = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
-			s_srcbin[d] = pno >= 0 ? a.cur.bin_offsets[pno] : -1;
+			sm.srcbin[d] = pno >= 0 ? a.cur.bin_offsets[pno] : -1;
 		}
 		{
-			float4* acc4 = reinterpret_cast<float4*>(s_acc);
-#pragma unroll
-			for(int i = tid; i < 8 * AS / 4; i += kG2P2GThreads) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+			float4* acc4 = reinterpret_cast<float4*>(sm.acc);
+			for(int i = tid; i < 8 * 256 / 4; i += T) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 		}
 		__syncthreads();
-		mbar_wait(&s_bar, phase);
+		mbar_wait(bar, phase);
 		phase ^= 1;
+		// SoA landing zone -> one float4 per node
+		for(int n = tid; n < 512; n += T) {
+			const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
+			const int o = (((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2)) * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
+			sm.vel4[n] = make_float4(sm.velsoa[o], sm.velsoa[o + 64], sm.velsoa[o + 128], 0.f);
+		}
+		__syncthreads();
 
 		const int dst_bin0 = a.next.bin_offsets[blk];
 		const int* __restrict__ bucket = a.next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
 
-		// ---- per-particle work -------------------------------------------------------------------
-		for(int pidib = tid; pidib < bucket_size; pidib += kG2P2GThreads) {
-			const int advect = __ldg(bucket + pidib);
-			const int dir = advect >> cfg.ppb_shift;
-			const int src_pidib = advect & ppb_mask;
-			const int sbin0 = s_srcbin[dir];
-			const float* __restrict__ sbin = a.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
+		for(int c0 = 0; c0 < bucket_size; c0 += kChunk) {
+			const int nchunk = min(kChunk, bucket_size - c0);
+			int cr0 = -1, cr1 = -1, cr2 = -1;  // (home cell << 16) | rank of the up-to-three particles of this thread
+			static_assert(ITERS <= 3, "cellrank registers");
 
-			float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
-			int base[3], ab[3];
-			float lp[3], w[3][3];
+			// ================= phase 1: particle-parallel ==============================================
+#pragma unroll 1
+			for(int it = 0; it < ITERS; ++it) {
+				const int slot = it * T + tid;
+				if(slot >= nchunk) continue;
+				const int pidib = c0 + slot;
+				const int advect = __ldg(bucket + pidib);
+				const int dir = advect >> cfg.ppb_shift;
+				const int src_pidib = advect & ppb_mask;
+				const int sbin0 = sm.srcbin[dir];
+				const float* __restrict__ sbin = a.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
+
+				float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
+				int base[3], ab[3];
+				float lp[3], w[3][3];
 #pragma unroll
-			for(int d = 0; d < 3; ++d) {
-				base[d] = cell_index(cfg, pos[d]) - 1;
-				lp[d] = pos[d] - base[d] * dx;
-				bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
-				ab[d] = ((base[d] - 1) & 3) + 1;
-			}
-			// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d])
-			float vel[3] = {0.f, 0.f, 0.f};
-			float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+				for(int d = 0; d < 3; ++d) {
+					base[d] = cell_index(cfg, pos[d]) - 1;
+					lp[d] = pos[d] - base[d] * dx;
+					bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
+					ab[d] = ((base[d] - 1) & 3) + 1;
+				}
+				// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d])
+				float vel[3] = {0.f, 0.f, 0.f};
+				float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+				const int nbase = (ab[0] * 8 + ab[1]) * 8 + ab[2];
 #pragma unroll
-			for(int i = 0; i < 3; ++i) {
-				const int ox = arena_off_x<VS>(ab[0] + i);
-				const float xx = i * dx - lp[0];
+				for(int i = 0; i < 3; ++i) {
+					const float xx = i * dx - lp[0];
 #pragma unroll
-				for(int j = 0; j < 3; ++j) {
-					const int oxy = ox + arena_off_y<VS>(ab[1] + j);
-					const float xy = j * dx - lp[1];
-					const float wij = w[0][i] * w[1][j];
+					for(int j = 0; j < 3; ++j) {
+						const float xy = j * dx - lp[1];
+						const float wij = w[0][i] * w[1][j];
 #pragma unroll
-					for(int k = 0; k < 3; ++k) {
-						const int o = oxy + arena_off_z<VS>(ab[2] + k);
-						const float xz = k * dx - lp[2];
-						const float W = wij * w[2][k];
-						const float v0 = s_vel[o], v1 = s_vel[o + 64], v2 = s_vel[o + 128];
-						const float wv0 = W * v0, wv1 = W * v1, wv2 = W * v2;
-						vel[0] += wv0;
-						vel[1] += wv1;
-						vel[2] += wv2;
-						A[0] += wv0 * xx;
-						A[1] += wv1 * xx;
-						A[2] += wv2 * xx;
-						A[3] += wv0 * xy;
-						A[4] += wv1 * xy;
-						A[5] += wv2 * xy;
-						A[6] += wv0 * xz;
-						A[7] += wv1 * xz;
-						A[8] += wv2 * xz;
+						for(int k = 0; k < 3; ++k) {
+							const float xz = k * dx - lp[2];
+							const float W = wij * w[2][k];
+							const float4 v = sm.vel4[nbase + i * 64 + j * 8 + k];
+							const float wv0 = W * v.x, wv1 = W * v.y, wv2 = W * v.z;
+							vel[0] += wv0;
+							vel[1] += wv1;
+							vel[2] += wv2;
+							A[0] += wv0 * xx;
+							A[1] += wv1 * xx;
+							A[2] += wv2 * xx;
+							A[3] += wv0 * xy;
+							A[4] += wv1 * xy;
+							A[5] += wv2 * xy;
+							A[6] += wv0 * xz;
+							A[7] += wv1 * xz;
+							A[8] += wv2 * xz;
+						}
 					}
 				}
-			}
 #pragma unroll
-			for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+				for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
 
-			float contrib[9];
-			float* __restrict__ dbin = a.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
-			if constexpr(MAT == CB200_J_FLUID) {
-				float J = __ldg(sbin + 96);
-				J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
-				if(J < 0.1f) J = 0.1f;
-				const float voln = J * a.mat.volume;
-				const float pressure = a.mat.bulk * (powf(J, -a.mat.gamma) - 1.f);
-				const float vs = d_inv * a.mat.viscosity;
-				contrib[0] = ((A[0] + A[0]) * vs - pressure) * voln;
-				contrib[1] = (A[1] + A[3]) * vs * voln;
-				contrib[2] = (A[2] + A[6]) * vs * voln;
-				contrib[3] = contrib[1];
-				contrib[4] = ((A[4] + A[4]) * vs - pressure) * voln;
-				contrib[5] = (A[5] + A[7]) * vs * voln;
-				contrib[6] = contrib[2];
-				contrib[7] = contrib[5];
-				contrib[8] = ((A[8] + A[8]) * vs - pressure) * voln;
-				dbin[0] = pos[0];
-				dbin[32] = pos[1];
-				dbin[64] = pos[2];
-				dbin[96] = J;
-			} else {
-				float Fo[9], F[9], G[9];
-#pragma unroll
-				for(int d = 0; d < 9; ++d) Fo[d] = __ldg(sbin + (3 + d) * 32);
-				const float sc = dt * d_inv;
-#pragma unroll
-				for(int d = 0; d < 9; ++d) G[d] = A[d] * sc + ((d & 3) ? 0.f : 1.f);
-#pragma unroll
-				for(int c = 0; c < 3; ++c)
-#pragma unroll
-					for(int r = 0; r < 3; ++r) F[r + 3 * c] = G[r] * Fo[3 * c] + G[r + 3] * Fo[3 * c + 1] + G[r + 6] * Fo[3 * c + 2];
-				dbin[0] = pos[0];
-				dbin[32] = pos[1];
-				dbin[64] = pos[2];
-				if constexpr(MAT == CB200_FIXED_COROTATED) {
-#pragma unroll
-					for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
-					stress_fixed_corotated(a.mat, F, contrib);
+				float contrib[9];
+				float* __restrict__ dbin = a.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
+				if constexpr(MAT == CB200_J_FLUID) {
+					float J = __ldg(sbin + 96);
+					J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
+					if(J < 0.1f) J = 0.1f;
+					const float voln = J * a.mat.volume;
+					const float pressure = a.mat.bulk * (powf(J, -a.mat.gamma) - 1.f);
+					const float vs = d_inv * a.mat.viscosity;
+					contrib[0] = ((A[0] + A[0]) * vs - pressure) * voln;
+					contrib[1] = (A[1] + A[3]) * vs * voln;
+					contrib[2] = (A[2] + A[6]) * vs * voln;
+					contrib[3] = contrib[1];
+					contrib[4] = ((A[4] + A[4]) * vs - pressure) * voln;
+					contrib[5] = (A[5] + A[7]) * vs * voln;
+					contrib[6] = contrib[2];
+					contrib[7] = contrib[5];
+					contrib[8] = ((A[8] + A[8]) * vs - pressure) * voln;
+					dbin[0] = pos[0];
+					dbin[32] = pos[1];
+					dbin[64] = pos[2];
+					dbin[96] = J;
 				} else {
-					float log_jp = __ldg(sbin + 12 * 32);
-					if constexpr(MAT == CB200_SAND) stress_sand(a.mat, F, contrib, log_jp);
-					else stress_nacc(a.mat, F, contrib, log_jp);
+					float Fo[9], F[9], G[9];
 #pragma unroll
-					for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
-					dbin[12 * 32] = log_jp;
-				}
-			}
-			const float mass = a.mat.mass;
+					for(int d = 0; d < 9; ++d) Fo[d] = __ldg(sbin + (3 + d) * 32);
+					const float sc = dt * d_inv;
 #pragma unroll
-			for(int d = 0; d < 9; ++d) contrib[d] = (A[d] * mass - contrib[d] * new_dt) * d_inv;
-
-			// ---- re-bucket (add_advection) -------------------------------------------------------
-			int nb[3], rel[3], cell[3];
-			bool far = false;
+					for(int d = 0; d < 9; ++d) G[d] = A[d] * sc + ((d & 3) ? 0.f : 1.f);
 #pragma unroll
-			for(int d = 0; d < 3; ++d) {
-				nb[d] = cell_index(cfg, pos[d]) - 1;
-				lp[d] = pos[d] - nb[d] * dx;
-				cell[d] = nb[d] - 1;
-			}
-			rel[0] = (cell[0] >> 2) - kx;
-			rel[1] = (cell[1] >> 2) - ky;
-			rel[2] = (cell[2] >> 2) - kz;
+					for(int c = 0; c < 3; ++c)
 #pragma unroll
-			for(int d = 0; d < 3; ++d) far |= (rel[d] < -1) | (rel[d] > 1);
-			if(!far) {
-				const int bno = s_nbr[(rel[0] + 1) * 9 + (rel[1] + 1) * 3 + rel[2] + 1];
-				if(bno >= 0) {
-					const int dirtag = (1 - rel[0]) * 9 + (1 - rel[1]) * 3 + (1 - rel[2]);
-					const int cellno = ((cell[0] & 3) << 4) | ((cell[1] & 3) << 2) | (cell[2] & 3);
-					int* cnt = a.next.cell_particle_counts + (size_t) bno * kBlockVol + cellno;
-					const int slot = atomicAdd(cnt, 1);
-					if(slot >= cfg.max_ppc) {
-						atomicSub(cnt, 1);
-						if(a.error) atomicOr(a.error, kErrCellOverflow);
+						for(int r = 0; r < 3; ++r) F[r + 3 * c] = G[r] * Fo[3 * c] + G[r + 3] * Fo[3 * c + 1] + G[r + 6] * Fo[3 * c + 2];
+					dbin[0] = pos[0];
+					dbin[32] = pos[1];
+					dbin[64] = pos[2];
+					if constexpr(MAT == CB200_FIXED_COROTATED) {
+#pragma unroll
+						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
+						stress_fixed_corotated(a.mat, F, contrib);
 					} else {
-						a.next.cellbuckets[((size_t) bno << cfg.ppb_shift) + (cellno << cfg.ppc_shift) + slot] = (dirtag << cfg.ppb_shift) | pidib;
+						float log_jp = __ldg(sbin + 12 * 32);
+						if constexpr(MAT == CB200_SAND) stress_sand(a.mat, F, contrib, log_jp);
+						else stress_nacc(a.mat, F, contrib, log_jp);
+#pragma unroll
+						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
+						dbin[12 * 32] = log_jp;
+					}
+				}
+#pragma unroll
+				for(int d = 0; d < 9; ++d) contrib[d] = (A[d] * mass - contrib[d] * new_dt) * d_inv;
+
+				// ---- re-bucket (add_advection) ---------------------------------------------------
+				int nb[3], rel[3], cell[3];
+				bool far = false;
+#pragma unroll
+				for(int d = 0; d < 3; ++d) {
+					nb[d] = cell_index(cfg, pos[d]) - 1;
+					lp[d] = pos[d] - nb[d] * dx;
+					cell[d] = nb[d] - 1;
+				}
+				rel[0] = (cell[0] >> 2) - kx;
+				rel[1] = (cell[1] >> 2) - ky;
+				rel[2] = (cell[2] >> 2) - kz;
+#pragma unroll
+				for(int d = 0; d < 3; ++d) far |= (rel[d] < -1) | (rel[d] > 1);
+				if(!far) {
+					const int bno = sm.nbr[(rel[0] + 1) * 9 + (rel[1] + 1) * 3 + rel[2] + 1];
+					if(bno >= 0) {
+						const int dirtag = (1 - rel[0]) * 9 + (1 - rel[1]) * 3 + (1 - rel[2]);
+						const int cellno = ((cell[0] & 3) << 4) | ((cell[1] & 3) << 2) | (cell[2] & 3);
+						int* cnt = a.next.cell_particle_counts + (size_t) bno * kBlockVol + cellno;
+						const int s = atomicAdd(cnt, 1);
+						if(s >= cfg.max_ppc) {
+							atomicSub(cnt, 1);
+							if(a.error) atomicOr(a.error, kErrCellOverflow);
+						} else {
+							a.next.cellbuckets[((size_t) bno << cfg.ppb_shift) + (cellno << cfg.ppc_shift) + s] = (dirtag << cfg.ppb_shift) | pidib;
+						}
+					} else if(a.error) {
+						atomicOr(a.error, kErrLostParticle);
 					}
 				} else if(a.error) {
 					atomicOr(a.error, kErrLostParticle);
 				}
-			} else if(a.error) {
-				atomicOr(a.error, kErrLostParticle);
-			}
 
-			// ---- P2G into the shared arena -------------------------------------------------------
-			bool oob = false;
+				// ---- stage the P2G record ----------------------------------------------------------
+				int nab[3];
+				bool oob = false, moved = false;
 #pragma unroll
-			for(int d = 0; d < 3; ++d) {
-				bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
-				ab[d] = ab[d] + (nb[d] - base[d]);
-				oob |= (ab[d] < 0) | (ab[d] > 5);
+				for(int d = 0; d < 3; ++d) {
+					nab[d] = ab[d] + (nb[d] - base[d]);
+					oob |= (nab[d] < 0) | (nab[d] > 5);
+					moved |= nb[d] != base[d];
+				}
+				int code = (nab[0] & 7) | ((nab[1] & 7) << 3) | ((nab[2] & 7) << 6);
+				if(oob) {  // moved more than one cell: the reference drops the contribution (mgmpm_kernels.cuh:881-885)
+					code = kRecDrop;
+					if(a.error) atomicOr(a.error, kErrLostParticle);
+				} else if(moved) {
+					code |= kRecMover;
+					sm.movers[atomicAdd(&sm.nmovers, 1)] = (unsigned short) slot;
+				}
+				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
+				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
+				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
+				sm.rec[0][slot] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
+				sm.rec[1][slot] = make_float4(q0, q1, q2, contrib[0] * dx);
+				sm.rec[2][slot] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
+				sm.rec[3][slot] = make_float4(contrib[5] * dx, contrib[6] * dx, contrib[7] * dx, contrib[8] * dx);
+				// counting sort by the cell the particle came from (its accumulation home)
+				const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
+				const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);
+				if(it == 0) cr0 = cr;
+				else if(it == 1) cr1 = cr;
+				else cr2 = cr;
 			}
-			if(oob) {  // moved more than one cell: the reference drops the contribution (mgmpm_kernels.cuh:881-885)
-				if(a.error) atomicOr(a.error, kErrLostParticle);
-				continue;
+			__syncthreads();
+			if(tid < 32) {
+				const int c0v = sm.cnt[2 * tid], c1v = sm.cnt[2 * tid + 1];
+				const int pair = c0v + c1v;
+				int inc = pair;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1) {
+					const int t = __shfl_up_sync(0xffffffffu, inc, o);
+					if(tid >= o) inc += t;
+				}
+				sm.start[2 * tid] = inc - pair;
+				sm.start[2 * tid + 1] = inc - pair + c0v;
+				if(tid == 31) sm.start[64] = inc;
 			}
+			__syncthreads();
+			if(cr0 >= 0) sm.idx[sm.start[cr0 >> 16] + (cr0 & 0xffff)] = (unsigned short) tid;
+			if(cr1 >= 0) sm.idx[sm.start[cr1 >> 16] + (cr1 & 0xffff)] = (unsigned short) (T + tid);
+			if(cr2 >= 0) sm.idx[sm.start[cr2 >> 16] + (cr2 & 0xffff)] = (unsigned short) (2 * T + tid);
+			__syncthreads();
+
+			// ================= phase 2: cell-parallel accumulation =====================================
+			{
+				const int hc = tid / 3, sl = tid - 3 * hc;
+				const int n = sm.cnt[hc], st = sm.start[hc];
+				float pa, pb, pc;
+				bspline_poly(sl, pa, pb, pc);
+				const float fi = (float) sl;
+				float acc[9][4];
 #pragma unroll
-			for(int i = 0; i < 3; ++i) {
-				const int ox = arena_off_x<AS>(ab[0] + i);
-				const float xx = i * dx - lp[0];
+				for(int n9 = 0; n9 < 9; ++n9) acc[n9][0] = acc[n9][1] = acc[n9][2] = acc[n9][3] = 0.f;
+				for(int p = 0; p < n; ++p) {
+					const int slot = sm.idx[st + p];
+					const float4 r0 = sm.rec[0][slot];
+					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
+					const float4 r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
+					const float wx = pa + r0.x * (pb + pc * r0.x);
+					float wy[3], wz[3];
+					bspline_weights(r0.y, wy[0], wy[1], wy[2]);
+					bspline_weights(r0.z, wz[0], wz[1], wz[2]);
+					// D (= contrib * dx, column-major c + 3d): r1.w r2.x r2.y | r2.z r2.w r3.x | r3.y r3.z r3.w
+					const float t0 = r1.x + fi * r1.w, t1 = r1.y + fi * r2.x, t2 = r1.z + fi * r2.y;
 #pragma unroll
-				for(int j = 0; j < 3; ++j) {
-					const int oxy = ox + arena_off_y<AS>(ab[1] + j);
-					const float xy = j * dx - lp[1];
-					const float wij = w[0][i] * w[1][j];
+					for(int j = 0; j < 3; ++j) {
+						const float wxy = wx * wy[j];
+						const float u0 = t0 + j * r2.z, u1 = t1 + j * r2.w, u2 = t2 + j * r3.x;
 #pragma unroll
-					for(int k = 0; k < 3; ++k) {
-						const int o = oxy + arena_off_z<AS>(ab[2] + k);
-						const float xz = k * dx - lp[2];
-						const float W = wij * w[2][k];
-						const float wm = mass * W;
-						atomicAdd(&s_acc[o], wm);
-						atomicAdd(&s_acc[o + 64], wm * vel[0] + (contrib[0] * xx + contrib[3] * xy + contrib[6] * xz) * W);
-						atomicAdd(&s_acc[o + 128], wm * vel[1] + (contrib[1] * xx + contrib[4] * xy + contrib[7] * xz) * W);
-						atomicAdd(&s_acc[o + 192], wm * vel[2] + (contrib[2] * xx + contrib[5] * xy + contrib[8] * xz) * W);
+						for(int k = 0; k < 3; ++k) {
+							const float W = wxy * wz[k];
+							acc[j * 3 + k][0] += W;
+							acc[j * 3 + k][1] += W * (u0 + k * r3.y);
+							acc[j * 3 + k][2] += W * (u1 + k * r3.z);
+							acc[j * 3 + k][3] += W * (u2 + k * r3.w);
+						}
+					}
+				}
+				if(n > 0) {
+					const int X = (hc >> 4) + 1 + sl, Y = ((hc >> 2) & 3) + 1, Z = (hc & 3) + 1;
+					const int ox = acc_off_x(X);
+#pragma unroll
+					for(int j = 0; j < 3; ++j) {
+						const int oxy = ox + acc_off_y(Y + j);
+#pragma unroll
+						for(int k = 0; k < 3; ++k) {
+							const int o = oxy + acc_off_z(Z + k);
+							atomicAdd(&sm.acc[o], mass * acc[j * 3 + k][0]);
+							atomicAdd(&sm.acc[o + 64], acc[j * 3 + k][1]);
+							atomicAdd(&sm.acc[o + 128], acc[j * 3 + k][2]);
+							atomicAdd(&sm.acc[o + 192], acc[j * 3 + k][3]);
+						}
 					}
 				}
 			}
+			// ================= phase 3: particles that changed cell, node-parallel ====================
+			{
+				const int total = sm.nmovers * 27;
+				for(int wk = tid; wk < total; wk += T) {
+					const int m = wk / 27, nn = wk - 27 * m;
+					const int i = nn / 9, j = (nn / 3) % 3, k = nn % 3;
+					const int slot = sm.movers[m];
+					const float4 r0 = sm.rec[0][slot], r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
+					const int code = __float_as_int(r0.w);
+					float pa, pb, pc;
+					bspline_poly(i, pa, pb, pc);
+					const float wx = pa + r0.x * (pb + pc * r0.x);
+					bspline_poly(j, pa, pb, pc);
+					const float wy = pa + r0.y * (pb + pc * r0.y);
+					bspline_poly(k, pa, pb, pc);
+					const float wz = pa + r0.z * (pb + pc * r0.z);
+					const float W = wx * wy * wz;
+					const float fi = (float) i, fj = (float) j, fk = (float) k;
+					const int o = acc_off_x((code & 7) + i) + acc_off_y(((code >> 3) & 7) + j) + acc_off_z(((code >> 6) & 7) + k);
+					atomicAdd(&sm.acc[o], mass * W);
+					atomicAdd(&sm.acc[o + 64], W * (r1.x + fi * r1.w + fj * r2.z + fk * r3.y));
+					atomicAdd(&sm.acc[o + 128], W * (r1.y + fi * r2.x + fj * r2.w + fk * r3.z));
+					atomicAdd(&sm.acc[o + 192], W * (r1.z + fi * r2.y + fj * r3.x + fk * r3.w));
+				}
+			}
+			__syncthreads();
+			if(tid < 64) sm.cnt[tid] = 0;
+			if(tid == 64) sm.nmovers = 0;
+			__syncthreads();
 		}
 
 		// ---- arena -> next grid: eight 1-KiB bulk add-reductions ----------------------------------
@@ -310,7 +456,7 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 		__syncthreads();
 		if(tid < 8) {
 			const int bno = table_query(cfg, a.table, kx + ((tid >> 2) & 1), ky + ((tid >> 1) & 1), kz + (tid & 1));
-			if(bno >= 0) tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, s_acc + tid * AS, AS * 4);
+			if(bno >= 0) tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
 			tma_commit();
 			tma_wait_read<0>();
 		}
