@@ -18,6 +18,7 @@
 #include "g2p2g.cuh"
 #include "grid.cuh"
 #include "init.cuh"
+#include "mgsp.cuh"
 #include "partition.cuh"
 
 namespace cb200 {
@@ -88,6 +89,13 @@ struct cb200_sim {
 	// MGSP
 	int* peer_overlap_keys = nullptr;   // blockids of my blocks overlapping each peer: [world][max_blocks*3]
 	int* peer_overlap_count = nullptr;  // [world]
+	InboxLayout inbox_layout {};
+	unsigned char* inbox_local = nullptr;
+	unsigned char* inbox_peer[kMaxRanks] = {};
+	bool inbox_opened[kMaxRanks] = {};
+	bool peers_ready = false;
+	int* mgsp_done = nullptr;    // [4] last-CTA counters
+	int* mgsp_epochs = nullptr;  // [3]
 	// per-kernel timing (cudaEvent pairs around the g2p2g launches; stream mode only)
 	bool profiling = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -318,9 +326,58 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 	return (int) cudaGetLastError();
 }
 
+// ---- MGSP exchange phases ----------------------------------------------------------------------------------
+MgspView mgsp_view(cb200_sim* s) {
+	MgspView v {};
+	v.L = s->inbox_layout;
+	v.rank = s->desc.mgsp_rank;
+	v.world = s->desc.mgsp_world;
+	for(int r = 0; r < v.world; ++r) v.inbox[r] = s->inbox_peer[r];
+	v.overlap_keys = s->peer_overlap_keys;
+	v.overlap_count = s->peer_overlap_count;
+	v.done = s->mgsp_done;
+	v.epochs = s->mgsp_epochs;
+	return v;
+}
+// collect_halo_grid_blocks + reduce_halo_grid_blocks (mgsp_benchmark.cuh:723-776) on grid `g`, numbering of partition `P`
+int enqueue_halo_send(cb200_sim* s, int g, int P) {
+	mgsp_pack_send_kernel<<<grid_blocks(2), 256, 0, s->stream>>>(s->cfg, mgsp_view(s), s->grid[g], s->part[P].index_table);
+	++s->launches;
+	return (int) cudaGetLastError();
+}
+int enqueue_halo_reduce(cb200_sim* s, int g, int P) {
+	mgsp_wait_reduce_kernel<<<grid_blocks(2), 256, 0, s->stream>>>(s->cfg, mgsp_view(s), s->grid[g], s->part[P].index_table, &s->d_state->error);
+	++s->launches;
+	return (int) cudaGetLastError();
+}
+// halo_tagging (mgsp_benchmark.cuh:661-720) on partition P whose Partition::count currently equals its neighbour count
+int enqueue_halo_tagging(cb200_sim* s, int P, const int* particle_block_count) {
+	cudaStream_t st = s->stream;
+	const MgspView v = mgsp_view(s);
+	mgsp_tag_reset_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].overlap_marks, s->part[P].count, s->part[P].halo_count);
+	mgsp_publish_keys_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].active_keys, s->part[P].count);
+	mgsp_tag_kernel<<<grid_blocks(1), 256, 0, st>>>(s->cfg, v, s->part[P].index_table, s->part[P].overlap_marks);
+	collect_halo_blockids_kernel<<<grid_blocks(2), 128, 0, st>>>(s->cfg, count_dev(particle_block_count), s->part[P].index_table, s->part[P].active_keys, s->part[P].overlap_marks, s->part[P].halo_marks, s->part[P].halo_count, nullptr);
+	s->launches += 4;
+	return (int) cudaGetLastError();
+}
+
 int enqueue_substep(cb200_sim* s, int R) {
 	int e;
 	if((e = enqueue_grid_update(s, R))) return e;
+	if(s->desc.mgsp_world > 1) {
+		// dt must be the same on every rank: all-reduce(max) of |v|^2 (host max over devices in the reference, :410-416)
+		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s), &s->d_state->max_vel_sq);
+		++s->launches;
+		if((e = enqueue_g2p2g(s, R, 1))) return e;         // halo particle blocks first            (:421-446)
+		if((e = enqueue_halo_send(s, 1, R))) return e;      // their next-grid blocks go to the peers (:449)
+		if((e = enqueue_g2p2g(s, R, 2))) return e;         // the rest overlaps the transfer         (:451-464)
+		if((e = enqueue_halo_reduce(s, 1, R))) return e;    // add what arrived                        (:467)
+		if((e = enqueue_rebuild(s, R))) return e;
+		if((e = enqueue_halo_tagging(s, R ^ 1, s->d_scratch + 0))) return e;  // (:530)
+		if((e = enqueue_carry_and_exterior(s, R))) return e;
+		return 0;
+	}
 	if((e = enqueue_g2p2g(s, R, 0))) return e;
 	if((e = enqueue_rebuild(s, R))) return e;
 	if((e = enqueue_carry_and_exterior(s, R))) return e;
@@ -358,9 +415,19 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 	CK(cudaMalloc(&s->d_scratch, 16 * sizeof(int)));
 	CK(cudaMemsetAsync(s->d_scratch, 0, 16 * sizeof(int), s->stream));
 	if(s->desc.mgsp_world > 1) {
-		CK(cudaMalloc(&s->peer_overlap_keys, (size_t) s->desc.mgsp_world * (mb + 1) * 3 * sizeof(int)));
+		if(s->desc.mgsp_world > kMaxRanks || s->desc.mgsp_rank < 0 || s->desc.mgsp_rank >= s->desc.mgsp_world) return (int) cudaErrorInvalidValue;
+		if(s->desc.mgsp_halo_cap <= 0) s->desc.mgsp_halo_cap = desc->max_blocks / 2;
+		CK(cudaMalloc(&s->peer_overlap_keys, (size_t) s->desc.mgsp_world * mb * 3 * sizeof(int)));
 		CK(cudaMalloc(&s->peer_overlap_count, (size_t) s->desc.mgsp_world * sizeof(int)));
 		CK(cudaMemsetAsync(s->peer_overlap_count, 0, (size_t) s->desc.mgsp_world * sizeof(int), s->stream));
+		s->inbox_layout = make_inbox_layout(s->desc.mgsp_world, s->desc.mgsp_halo_cap, desc->max_blocks);
+		CK(cudaMalloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
+		CK(cudaMemsetAsync(s->inbox_local, 0, inbox_bytes(s->inbox_layout), s->stream));
+		s->inbox_peer[s->desc.mgsp_rank] = s->inbox_local;
+		CK(cudaMalloc(&s->mgsp_done, 8 * sizeof(int)));
+		CK(cudaMemsetAsync(s->mgsp_done, 0, 8 * sizeof(int), s->stream));
+		s->mgsp_epochs = s->mgsp_done + 4;
+		CK(cudaStreamSynchronize(s->stream));
 	}
 	*out = s;
 	return 0;
@@ -396,6 +463,10 @@ int cb200_sim_destroy(cb200_sim* s) {
 	cudaFree(s->d_state);
 	cudaFree(s->peer_overlap_keys);
 	cudaFree(s->peer_overlap_count);
+	for(int r = 0; r < kMaxRanks; ++r)
+		if(s->inbox_opened[r]) cudaIpcCloseMemHandle(s->inbox_peer[r]);
+	cudaFree(s->inbox_local);
+	cudaFree(s->mgsp_done);
 	cudaFreeHost(s->h_state);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
@@ -522,6 +593,11 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 		register_blocks_kernel<<<blocks_for((long long) pbc * 8, 128), 128, 0, st>>>(a);
 		CK(cudaMemcpyAsync(&nbc, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		if(s->desc.mgsp_world > 1) {  // halo_tagging of the initial partition (mgsp_benchmark.cuh:633)
+			if(!s->peers_ready) return (int) cudaErrorNotReady;
+			CK(cudaMemcpyAsync(s->d_scratch + 0, &pbc, sizeof(int), cudaMemcpyHostToDevice, st));
+			CK(enqueue_halo_tagging(s, Rn, s->d_scratch + 0));
+		}
 		a.lo = -1;
 		a.span = 3;
 		register_blocks_kernel<<<blocks_for((long long) pbc * 27, 128), 128, 0, st>>>(a);
@@ -535,6 +611,11 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	CK(cudaMemcpyAsync(s->part[R].index_table, s->part[Rn].index_table, s->table_entries * sizeof(int), cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemcpyAsync(s->part[R].active_keys, s->part[Rn].active_keys, (size_t) ebc * 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemcpyAsync(s->part[R].count, s->part[Rn].count, sizeof(int), cudaMemcpyDeviceToDevice, st));
+	if(s->desc.mgsp_world > 1) {  // "need to copy halo tag info as well" (mgsp_benchmark.cuh:639-640)
+		CK(cudaMemcpyAsync(s->part[R].halo_marks, s->part[Rn].halo_marks, (size_t) pbc, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s->part[R].overlap_marks, s->part[Rn].overlap_marks, (size_t) nbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s->part[R].halo_count, s->part[Rn].halo_count, sizeof(int), cudaMemcpyDeviceToDevice, st));
+	}
 	for(Model& m : s->models) {
 		CK(cudaMemcpyAsync(m.pb[Rn].bin_offsets, m.pb[R].bin_offsets, (size_t) (pbc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
 		CK(cudaMemcpyAsync(m.pb[Rn].particle_bucket_sizes, m.pb[R].particle_bucket_sizes, (size_t) pbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -547,6 +628,10 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 		s->launches += 2;
 	}
 	CK(cudaGetLastError());
+	if(s->desc.mgsp_world > 1) {  // the rasterised halo blocks are partial sums: reduce them (mgsp_benchmark.cuh:653-654)
+		CK(enqueue_halo_send(s, 0, R));
+		CK(enqueue_halo_reduce(s, 0, R));
+	}
 	// device-resident step state; initial dt as in main_loop's preamble (gmpm_simulator.cuh:305-315)
 	CK(pull_state(s));
 	StepState& h = *s->h_state;
@@ -560,6 +645,14 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	h.step_time = 0.f;
 	float mv = 0.f;
 	for(const Model& m : s->models) mv = fmaxf(mv, sqrtf(m.v0[0] * m.v0[0] + m.v0[1] * m.v0[1] + m.v0[2] * m.v0[2]));
+	if(s->desc.mgsp_world > 1) {  // every rank must start from the same dt: max over the ranks' initial speeds
+		h.max_vel_sq = mv * mv;
+		CK(push_state(s));
+		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, st>>>(mgsp_view(s), &s->d_state->max_vel_sq);
+		++s->launches;
+		CK(pull_state(s));
+		mv = sqrtf(s->h_state->max_vel_sq);
+	}
 	float dt = h.dt_default;
 	if(mv > 0.f) dt = fminf(dt, cfg.dx * cfg.cfl / mv);
 	if(h.frame_time > 0.f) dt = fminf(dt, h.frame_time);
@@ -696,6 +789,50 @@ int cb200_sim_grid(cb200_sim* s, float* grid_host, int capacity_blocks, int* n_o
 	return 0;
 }
 long long cb200_sim_launch_count(cb200_sim* s) { return s ? s->launches : 0; }
+
+// ---- MGSP peer wiring ------------------------------------------------------------------------------------------
+int cb200_sim_mgsp_inbox(cb200_sim* s, void** ptr, size_t* bytes) {
+	if(!s || s->desc.mgsp_world <= 1) return (int) cudaErrorInvalidValue;
+	if(ptr) *ptr = s->inbox_local;
+	if(bytes) *bytes = inbox_bytes(s->inbox_layout);
+	return 0;
+}
+int cb200_sim_mgsp_ipc_handle(cb200_sim* s, void* handle64) {
+	if(!s || s->desc.mgsp_world <= 1 || !handle64) return (int) cudaErrorInvalidValue;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, s->inbox_local));
+	memcpy(handle64, &h, 64);
+	return 0;
+}
+int cb200_sim_mgsp_open_peers(cb200_sim* s, const void* handles) {
+	if(!s || s->desc.mgsp_world <= 1 || !handles) return (int) cudaErrorInvalidValue;
+	for(int r = 0; r < s->desc.mgsp_world; ++r) {
+		if(r == s->desc.mgsp_rank) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const unsigned char*) handles + 64 * r, 64);
+		void* p = nullptr;
+		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		s->inbox_peer[r] = (unsigned char*) p;
+		s->inbox_opened[r] = true;
+	}
+	s->peers_ready = true;
+	return 0;
+}
+int cb200_sim_mgsp_set_peers(cb200_sim* s, void* const* ptrs) {
+	if(!s || s->desc.mgsp_world <= 1 || !ptrs) return (int) cudaErrorInvalidValue;
+	for(int r = 0; r < s->desc.mgsp_world; ++r)
+		if(r != s->desc.mgsp_rank) s->inbox_peer[r] = (unsigned char*) ptrs[r];
+	s->peers_ready = true;
+	return 0;
+}
+int cb200_sim_mgsp_halo_counts(cb200_sim* s, int* shared, int* halo_particle_blocks) {
+	if(!s || s->desc.mgsp_world <= 1) return (int) cudaErrorInvalidValue;
+	CK(cudaStreamSynchronize(s->stream));
+	if(shared) CK(cudaMemcpy(shared, s->peer_overlap_count, s->desc.mgsp_world * sizeof(int), cudaMemcpyDeviceToHost));
+	if(halo_particle_blocks) CK(cudaMemcpy(halo_particle_blocks, s->part[s->rollid].halo_count, sizeof(int), cudaMemcpyDeviceToHost));
+	return 0;
+}
 
 // per-kernel timing for the roofline: CUDA-event pairs around every g2p2g launch (sub-steps are issued as plain
 // stream launches while profiling is on, so the events bracket exactly one kernel each)

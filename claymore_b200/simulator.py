@@ -18,12 +18,13 @@ class GmpmSimulator:
     DEFAULT_FRAMES = 60   # :26
 
     def __init__(self, gpu=0, dt=DEFAULT_DT, fps=DEFAULT_FPS, frames=DEFAULT_FRAMES, config=None, max_blocks=10000, use_graph=True,
-                 stream=None, mgsp_rank=0, mgsp_world=1):
+                 stream=None, mgsp_rank=0, mgsp_world=1, mgsp_halo_cap=0):
         self.L = lib()
         self.gpu = gpu
         self.cfg = config if config is not None else Config()
         self.fps, self.nframes = fps, frames
-        self.desc = SimDesc(self.cfg, dt, fps, max_blocks, 1 if use_graph else 0, mgsp_rank, mgsp_world)
+        self.desc = SimDesc(self.cfg, dt, fps, max_blocks, 1 if use_graph else 0, mgsp_rank, mgsp_world, mgsp_halo_cap)
+        self.mgsp_rank, self.mgsp_world = mgsp_rank, mgsp_world
         self.max_blocks = max_blocks
         self._stream = C.c_void_p(stream) if stream else C.c_void_p(0)
         self.h = C.c_void_p()
@@ -129,6 +130,33 @@ class GmpmSimulator:
         n = C.c_int(0)
         check(self.L.cb200_sim_grid(self.h, out.ctypes.data_as(C.c_void_p), self.max_blocks, C.byref(n)), "grid")
         return out[: n.value]
+
+    # ---- MGSP peer wiring (one process per GPU: exchange the 64-byte IPC handles with any host all-gather) ----------
+    def mgsp_ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        check(self.L.cb200_sim_mgsp_ipc_handle(self.h, buf), "mgsp_ipc_handle")
+        return bytes(buf)
+
+    def mgsp_open_peers(self, handles_by_rank):
+        blob = b"".join(handles_by_rank)
+        assert len(blob) == 64 * self.mgsp_world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.L.cb200_sim_mgsp_open_peers(self.h, buf), "mgsp_open_peers")
+
+    def mgsp_inbox(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self.L.cb200_sim_mgsp_inbox(self.h, C.byref(p), C.byref(n)), "mgsp_inbox")
+        return p.value, n.value
+
+    def mgsp_set_peers(self, inbox_ptrs_by_rank):
+        arr = (C.c_void_p * len(inbox_ptrs_by_rank))(*inbox_ptrs_by_rank)
+        check(self.L.cb200_sim_mgsp_set_peers(self.h, arr), "mgsp_set_peers")
+
+    def mgsp_halo_counts(self):
+        cnt = (C.c_int * max(self.mgsp_world, 1))()
+        hp = C.c_int(0)
+        check(self.L.cb200_sim_mgsp_halo_counts(self.h, cnt, C.byref(hp)), "mgsp_halo_counts")
+        return list(cnt), hp.value
 
     def profile(self, enable=True):
         """CUDA-event pairs around every g2p2g launch (sub-steps run as plain stream launches meanwhile)."""

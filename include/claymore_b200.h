@@ -150,6 +150,7 @@ typedef struct cb200_sim_desc {
 	int max_blocks;          /* G_MAX_ACTIVE_BLOCK */
 	int use_graph;           /* 1: replay sub-steps from CUDA graphs */
 	int mgsp_rank, mgsp_world; /* MGSP static partition: this shard / number of shards (1 = GMPM) */
+	int mgsp_halo_cap;         /* max grid blocks shared with one peer (0 = max_blocks / 2) */
 } cb200_sim_desc;
 
 typedef struct cb200_sim_stats {
@@ -191,24 +192,18 @@ CB200_API long long cb200_sim_launch_count(cb200_sim* sim);
 CB200_API int cb200_sim_profile(cb200_sim* sim, int enable);
 CB200_API int cb200_sim_profile_read(cb200_sim* sim, double* g2p2g_ms_total, int* launches);
 
-/* MGSP halo exchange hooks (one process per GPU; transport is the caller's: NCCL via torch.distributed).
- * Sequence per sub-step (mgsp_benchmark.cuh:421-467, 661-776):
- *   step_begin   : grid update (+dt), clear, halo-block g2p2g            (:372-446)
- *   halo_pack    : pack overlapping next-grid blocks for every peer      (collect_grid_blocks :723-754)
- *   step_interior: g2p2g on non-halo blocks (overlaps the transfer)      (:451-464)
- *   halo_reduce  : add received blocks                                   (reduce_grid_blocks :756-776)
- *   step_finish  : partition rebuild                                     (:469-543)
- *   halo_tag     : mark blocks that are active on a peer, given the peer's key list (halo_tagging :661-720) */
-CB200_API int cb200_sim_mgsp_step_begin(cb200_sim* sim);
-CB200_API int cb200_sim_mgsp_halo_pack(cb200_sim* sim, int peer, float* send_blocks, int* send_keys, int capacity_blocks, int* count_dev);
-CB200_API int cb200_sim_mgsp_step_interior(cb200_sim* sim);
-CB200_API int cb200_sim_mgsp_halo_reduce(cb200_sim* sim, const float* recv_blocks, const int* recv_keys, const int* count_dev, int capacity_blocks);
-CB200_API int cb200_sim_mgsp_step_finish(cb200_sim* sim);
-CB200_API int cb200_sim_mgsp_halo_tag_reset(cb200_sim* sim);
-CB200_API int cb200_sim_mgsp_halo_tag(cb200_sim* sim, int peer, const int* peer_keys, const int* peer_count_dev, int capacity_blocks);
-CB200_API int cb200_sim_mgsp_halo_tag_finish(cb200_sim* sim);
-/* device pointers the transport needs: this shard's neighbour-block keys + count, max_vel^2 scalar */
-CB200_API int cb200_sim_mgsp_pointers(cb200_sim* sim, int** keys_dev, int** nbc_dev, float** max_vel_sq_dev);
+/* MGSP static particle partition, one process per GPU (Projects/MGSP/mgsp_benchmark.cuh:309-559, 661-776).
+ * Each rank creates its simulator with mgsp_rank / mgsp_world set and registers ITS OWN particle set with
+ * init_model.  Halo grid blocks, the neighbour-key lists for halo tagging and max |v|^2 are exchanged by kernels that
+ * store into the peers' inboxes over NVLink (CUDA IPC mapped) and publish epoch flags: the transport needs no host
+ * calls per sub-step.  Setup: every rank publishes its inbox handle, all ranks open all handles (any host-side
+ * all-gather: torch.distributed here), then initial_setup / step run as in the single-GPU case. */
+CB200_API int cb200_sim_mgsp_inbox(cb200_sim* sim, void** ptr, size_t* bytes);
+CB200_API int cb200_sim_mgsp_ipc_handle(cb200_sim* sim, void* handle64);                /* cudaIpcMemHandle_t, 64 bytes */
+CB200_API int cb200_sim_mgsp_open_peers(cb200_sim* sim, const void* handles64_by_rank); /* world x 64 bytes */
+CB200_API int cb200_sim_mgsp_set_peers(cb200_sim* sim, void* const* inbox_ptrs_by_rank); /* same-process peers */
+/* halo statistics of the current partition (synchronises): blocks shared with each rank, halo particle blocks */
+CB200_API int cb200_sim_mgsp_halo_counts(cb200_sim* sim, int* shared_blocks_by_rank, int* halo_particle_blocks);
 
 #ifdef __cplusplus
 }

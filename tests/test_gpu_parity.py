@@ -223,3 +223,83 @@ def test_grid_update_kernel_differential(oracle, cuda_lib):
     gc = t_g.cpu().numpy()[: nbc * 256]
     assert np.allclose(gc, g0[: nbc * 256], rtol=1e-6, atol=1e-7)
     assert abs(float(t_mv.item()) - float(mv[0])) <= 1e-6 * max(1.0, float(mv[0]))
+
+
+# ---- MGSP: two particle shards, exchange through peer inboxes (both ranks on ONE GPU, one host thread each) -----------
+@pytest.mark.timeout(300)
+def test_mgsp_two_shards_match_single_domain(oracle, cuda_lib):
+    import threading
+    from claymore_b200 import mgsp
+    scene = scenes.small_cube()
+    osim = scenes.build_oracle(oracle, scene)
+    sims = []
+    for r in range(2):
+        part = mgsp.partition_scene(scene, r, 2)
+        sims.append(mgsp.build_rank_sim(part, r, 2, 1e-4, 4000, scenes.apply_material))
+    ptrs = [s.mgsp_inbox()[0] for s in sims]
+    for s in sims:
+        s.mgsp_set_peers(ptrs)
+    # initial_setup synchronises with the peer (halo tagging), so the two ranks need a host thread each, as in the
+    # reference (one worker thread per GPU, mgsp_benchmark.cuh:309-334)
+    errs = []
+
+    def run(s):
+        try:
+            s.initial_setup()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(s,)) for s in sims]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not errs and not any(t.is_alive() for t in th)
+
+    def check(label):
+        okeys, ogrid = osim.active_keys(), osim.grid()
+        oh, og = scenes.grid_by_key(okeys, ogrid)
+        lut = {int(h): i for i, h in enumerate(oh)}
+        total = np.zeros_like(og)
+        seen = np.zeros(len(og), bool)
+        shared_sets = []
+        for s in sims:
+            st = s.stats()
+            assert st.error == 0, (label, st.error)
+            k, g = s.active_keys(), s.grid()
+            shared_sets.append(set(int(h) for h in scenes.key_hash(k[: len(g)])))
+        common = shared_sets[0] & shared_sets[1]
+        assert len(common) > 0
+        scale = np.abs(og).max(axis=(0, 2), keepdims=True)
+        for s in sims:
+            k, g = s.active_keys(), s.grid()
+            for b, h in enumerate(scenes.key_hash(k[: len(g)])):
+                i = lut.get(int(h))
+                if i is None:
+                    assert np.abs(g[b]).max() == 0, label
+                    continue
+                if int(h) in common:   # halo block: both owners hold the full sum
+                    assert np.all(np.abs(g[b] - og[i]) <= 2e-4 * scale[0] + 1e-12), (label, "halo block differs from the single-domain block")
+                    if not seen[i]:
+                        total[i] = g[b]
+                else:
+                    total[i] += g[b]
+                seen[i] = True
+        assert np.all(np.abs(total - og) <= 2e-4 * scale + 1e-12), label
+        # particles: union of the shards == single domain
+        so = osim.particle_state(0)
+        se = np.concatenate([s.particle_state(0) for s in sims])
+        assert len(so) == len(se)
+        idx = scenes.match_particles(so, se, tol=3e-6)
+        assert np.abs(se[idx][:, 3:] - so[:, 3:]).max() <= 1e-4, label
+        assert abs(sims[0].stats().dt - sims[1].stats().dt) == 0.0
+
+    check("after setup")
+    for k in range(3):
+        osim.step(4)
+        for s in sims:
+            s.step(4)
+        for s in sims:
+            s.sync()
+        check(f"after {4 * (k + 1)} steps")
+    shared, halo_pb = sims[0].mgsp_halo_counts()
+    assert shared[1] > 0 and halo_pb > 0
+    for s in sims:
+        s.close()
