@@ -37,6 +37,14 @@ static int g2p2g_blocks_per_sm() {
 	return v;
 }
 
+// resolves occupancy / shared-memory attributes of every material up front (see preload_kernels in engine.cu)
+void g2p2g_prepare_all() {
+	g2p2g_blocks_per_sm<CB200_J_FLUID>();
+	g2p2g_blocks_per_sm<CB200_FIXED_COROTATED>();
+	g2p2g_blocks_per_sm<CB200_SAND>();
+	g2p2g_blocks_per_sm<CB200_NACC>();
+}
+
 // launches the material-specialised kernel on a persistent grid (a multiple of the SM count)
 cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaStream_t s) {
 	int per_sm = 0;

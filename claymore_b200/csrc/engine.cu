@@ -24,6 +24,7 @@
 namespace cb200 {
 int num_sms();
 cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaStream_t s);
+void g2p2g_prepare_all();
 }  // namespace cb200
 using namespace cb200;
 
@@ -385,10 +386,72 @@ int enqueue_substep(cb200_sim* s, int R) {
 }
 }  // namespace
 
+namespace {
+// CUDA loads kernels lazily on first launch and that load can synchronise the context.  A rank whose stream holds a
+// kernel spinning on a peer's flag must therefore never be the one that still has to load a kernel: load all up front.
+template<typename K>
+void preload(K k) {
+	cudaFuncAttributes a;
+	(void) cudaFuncGetAttributes(&a, k);
+}
+void preload_kernels() {
+	static bool done = false;
+	if(done) return;
+	done = true;
+	preload(g2p2g_kernel<CB200_J_FLUID>);
+	preload(g2p2g_kernel<CB200_FIXED_COROTATED>);
+	preload(g2p2g_kernel<CB200_SAND>);
+	preload(g2p2g_kernel<CB200_NACC>);
+	preload(grid_update_kernel);
+	preload(clear_grid_kernel);
+	preload(carry_grid_kernel);
+	preload(scan_kernel);
+	preload(block_summary_kernel);
+	preload(rebuild_kernel);
+	preload(register_blocks_kernel);
+	preload(finalize_step_kernel);
+	preload(snapshot_int_kernel);
+	preload(cell_bucket_to_block_kernel);
+	preload(compute_bin_capacity_kernel);
+	preload(activate_blocks_kernel);
+	preload(build_particle_cell_buckets_kernel);
+	preload(array_to_buffer_kernel);
+	preload(rasterize_kernel);
+	preload(init_adv_bucket_kernel);
+	preload(retrieve_kernel);
+	preload(collect_halo_blockids_kernel);
+	preload(mgsp_allreduce_maxvel_kernel);
+	preload(mgsp_pack_send_kernel);
+	preload(mgsp_wait_reduce_kernel);
+	preload(mgsp_publish_keys_kernel);
+	preload(mgsp_tag_reset_kernel);
+	preload(mgsp_tag_kernel);
+	g2p2g_prepare_all();
+}
+int ensure_graph(cb200_sim* s, int R) {
+	if(s->graph[R]) return 0;
+	const long long before = s->launches;
+	cudaGraph_t g = nullptr;
+	CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+	s->capturing = true;
+	const int e = enqueue_substep(s, R);
+	s->capturing = false;
+	const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+	if(e) return e;
+	CK(ce);
+	CK(cudaGraphInstantiate(&s->graph[R], g, 0));
+	cudaGraphDestroy(g);
+	s->launches_per_step = s->launches - before;
+	s->launches = before;
+	return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) {
 	if(!desc || !out || !cfg_valid(desc->cfg) || desc->max_blocks <= 0) return (int) cudaErrorInvalidValue;
+	preload_kernels();
 	cb200_sim* s = new cb200_sim();
 	s->desc = *desc;
 	if(s->desc.mgsp_world < 1) s->desc.mgsp_world = 1;
@@ -661,6 +724,10 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	h.max_vel_sq = 0.f;
 	CK(push_state(s));
 	CK(cudaStreamSynchronize(st));
+	if(s->desc.use_graph) {  // instantiate both roll parities now: never later, while a peer may be waiting on this rank
+		CK(ensure_graph(s, 0));
+		CK(ensure_graph(s, 1));
+	}
 	s->setup_done = true;
 	return 0;
 }
@@ -670,21 +737,7 @@ int cb200_sim_step(cb200_sim* s, int n) {
 	for(int i = 0; i < n; ++i) {
 		const int R = s->rollid;
 		if(s->desc.use_graph && !s->profiling) {
-			if(!s->graph[R]) {
-				const long long before = s->launches;
-				cudaGraph_t g = nullptr;
-				CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-				s->capturing = true;
-				const int e = enqueue_substep(s, R);
-				s->capturing = false;
-				const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
-				if(e) return e;
-				CK(ce);
-				CK(cudaGraphInstantiate(&s->graph[R], g, 0));
-				cudaGraphDestroy(g);
-				s->launches_per_step = s->launches - before;
-				s->launches = before;
-			}
+			CK(ensure_graph(s, R));
 			CK(cudaGraphLaunch(s->graph[R], s->stream));
 			s->launches += s->launches_per_step;
 		} else {
