@@ -250,3 +250,52 @@ def test_halo_protocol_two_shards_equals_single(oracle):
                 total[i] += grid[b]
             seen[i] = True
     assert np.allclose(total, sgrid, rtol=2e-4, atol=1e-6 * np.abs(sgrid).max())
+
+
+# ---- the oracle against outputs of the reference's OWN kernels (recorded on a B200 by tests/golden/make_ref_gpu_golden.py) ----
+REF_GPU_CASES = {
+    "fc_small_cube": (lambda: scenes.small_cube(material=scenes.FIXED_COROTATED), 1e-4),
+    "fluid_small_cube": (lambda: scenes.small_cube(material=scenes.J_FLUID), 1e-4),
+    "sand_small_cube": (lambda: scenes.small_cube(material=scenes.SAND), 1e-4),
+    "fc_two_cubes": (scenes.two_cubes_colliding, 2e-4),
+}
+
+
+def compare_with_ref_gpu_golden(sim, g, cp, nmodels, label, pos_tol=3e-6, f_tol=2e-4):
+    """sim: anything with block_counts/active_keys/grid/particle_state (oracle or engine).  The reference build uses
+    --use_fast_math (approximate division / powf / logf / expf), hence slightly wider tolerances than oracle-vs-engine."""
+    pbc, nbc, ebc = sim.block_counts()
+    assert (pbc, nbc, ebc) == tuple(int(x) for x in g[f"s{cp}_counts"]), label
+    h = scenes.key_hash(sim.active_keys())
+    assert np.array_equal(np.sort(h[:pbc]), g[f"s{cp}_keys_particle"]), label
+    assert np.array_equal(np.sort(h[pbc:nbc]), g[f"s{cp}_keys_neighbor"]), label
+    assert np.array_equal(np.sort(h[nbc:ebc]), g[f"s{cp}_keys_exterior"]), label
+    gh, gg = scenes.grid_by_key(sim.active_keys(), sim.grid())
+    assert np.array_equal(gh, g[f"s{cp}_grid_keys"])
+    ref = g[f"s{cp}_grid"]
+    assert np.allclose(gg[:, 0], ref[:, 0], rtol=2e-5, atol=2e-5 * ref[:, 0].max()), (label, "mass")
+    assert np.abs(gg[:, 1:] - ref[:, 1:]).max() <= 2e-4 * np.abs(ref[:, 1:]).max(), (label, "momentum", np.abs(gg[:, 1:] - ref[:, 1:]).max(), np.abs(ref[:, 1:]).max())
+    assert abs(gg[:, 0].sum(dtype=np.float64) - ref[:, 0].sum(dtype=np.float64)) <= 1e-5 * ref[:, 0].sum(dtype=np.float64)
+    for m in range(nmodels):
+        key = f"s{cp}_state{m}"
+        if key not in g:
+            continue
+        so, se = g[key], sim.particle_state(m)
+        assert len(so) == len(se)
+        idx = scenes.match_particles(so, se, tol=pos_tol)
+        if so.shape[1] > 3:
+            assert np.abs(se[idx][:, 3:] - so[:, 3:]).max() <= f_tol, (label, np.abs(se[idx][:, 3:] - so[:, 3:]).max())
+
+
+@pytest.mark.parametrize("name", sorted(REF_GPU_CASES))
+def test_oracle_matches_reference_gpu_golden(oracle, name):
+    make, dt = REF_GPU_CASES[name]
+    scene = make()
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), f"ref_gpu_{name}.npz"))
+    sim = scenes.build_oracle(oracle, scene, dt=dt)
+    done = 0
+    for cp in (0, 1, 5, 15):
+        sim.step(cp - done)
+        done = cp
+        compare_with_ref_gpu_golden(sim, g, cp, len(scene["models"]), f"{name} step {cp}")
+        assert abs(sim.dt - float(g[f"s{cp}_dt"][0])) <= 1e-9
