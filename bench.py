@@ -57,7 +57,7 @@ def workload(name, n_gpus):
 
 def max_blocks_for(scene):
     n = sum(len(m["pos"]) for m in scene["models"])
-    return int(max(4000, n / 512 * 4.0))
+    return int(max(4000, n / 512 * 2.5))
 
 
 class ClockSampler:
@@ -225,15 +225,16 @@ def run_b200(args):
 
     value = n_particles * args.steps / (ms_total * 1e-3) / 1e6
     per_model = [len(m["pos"]) for m in scene["models"]]
-    # algorithmic bytes of ONE g2p2g launch = particles of that model x B_p + particle blocks x 2048;
-    # launches alternate over the models, so the average launch moves the average model
-    alg_bytes_per_launch = (sum(per_model) * BYTES_BY_MATERIAL[material] + pbc * BLOCK_BYTES_G2P2G * len(per_model)) / len(per_model)
+    # algorithmic bytes of one sub-step's g2p2g work = particles x B_p + 2048 B per particle block that holds particles of a
+    # model; models of one material are handled by ONE launch, so launches per step = distinct materials
+    launches_per_step = max(g2p2g_launches, 1) / args.steps
+    alg_bytes_per_launch = (sum(per_model) * BYTES_BY_MATERIAL[material] + pbc * BLOCK_BYTES_G2P2G) / launches_per_step
     avg_launch_s = g2p2g_ms / max(g2p2g_launches, 1) * 1e-3
     peak, peak_kind = measured_peak_hbm()
     achieved = alg_bytes_per_launch / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "kernel": "g2p2g_kernel<FIXED_COROTATED>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
-                "launches_timed": g2p2g_launches, "share_of_step": g2p2g_ms / max(g2p2g_launches, 1) * len(per_model) / (ms_total / args.steps)}
+                "launches_timed": g2p2g_launches, "share_of_step": (g2p2g_ms / args.steps) / (ms_total / args.steps)}
     traffic_file = os.path.join(ROOT, "profiles", "g2p2g_traffic.json")
     if os.path.exists(traffic_file):
         try:

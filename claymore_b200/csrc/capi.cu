@@ -88,9 +88,10 @@ int cb200_g2p2g(const cb200_config* c, float dt, float new_dt, int pbc, cb200_pa
 	a.block_count = pbc;
 	a.halo_mode = 0;
 	a.halo_marks = nullptr;
-	a.cur = view(cur);
-	a.next = view(next);
-	a.mat = mat_of(cur);
+	a.n_models = 1;
+	a.m[0].cur = view(cur);
+	a.m[0].next = view(next);
+	a.m[0].mat = mat_of(cur);
 	a.prev_table = prev_partition.index_table;
 	a.table = partition.index_table;
 	a.keys = partition.active_keys;

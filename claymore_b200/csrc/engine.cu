@@ -143,16 +143,22 @@ int push_state(cb200_sim* s) {
 	return 0;
 }
 
-G2P2GArgs make_g2p2g_args(cb200_sim* s, const Model& m, int R, int halo_mode) {
+// one launch per material: all models of that material share the staged neighbourhood of a block
+G2P2GArgs make_g2p2g_args(cb200_sim* s, int material, int R, int halo_mode) {
 	const int Rn = R ^ 1;
 	G2P2GArgs a {};
 	a.cfg = s->cfg;
 	a.state = s->d_state;
 	a.halo_mode = halo_mode;
 	a.halo_marks = s->part[R].halo_marks;
-	a.cur = view(m.pb[R]);
-	a.next = view(m.pb[Rn]);
-	a.mat = mat_of(m.pb[R]);
+	a.n_models = 0;
+	for(const Model& m : s->models) {
+		if(m.material != material) continue;
+		G2P2GModel& gm = a.m[a.n_models++];
+		gm.cur = view(m.pb[R]);
+		gm.next = view(m.pb[Rn]);
+		gm.mat = mat_of(m.pb[R]);
+	}
 	a.prev_table = s->part[Rn].index_table;
 	a.table = s->part[R].index_table;
 	a.keys = s->part[R].active_keys;
@@ -180,8 +186,9 @@ int enqueue_grid_update(cb200_sim* s, int R) {
 }
 // ---- phase B: g2p2g --------------------------------------------------------------------------------
 int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode) {
-	for(const Model& m : s->models) {
-		const G2P2GArgs a = make_g2p2g_args(s, m, R, halo_mode);
+	for(int material = 0; material < 4; ++material) {
+		const G2P2GArgs a = make_g2p2g_args(s, material, R, halo_mode);
+		if(a.n_models == 0) continue;
 		const bool timed = s->profiling && !s->capturing;
 		if(timed) {
 			if(s->prof_used == s->prof_events.size()) {
@@ -192,7 +199,7 @@ int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode) {
 			}
 			CK(cudaEventRecord(s->prof_events[s->prof_used].first, s->stream));
 		}
-		CK(launch_g2p2g(m.material, a, -1, s->stream));
+		CK(launch_g2p2g(material, a, -1, s->stream));
 		if(timed) CK(cudaEventRecord(s->prof_events[s->prof_used++].second, s->stream));
 		++s->launches;
 	}

@@ -34,6 +34,10 @@ namespace cb200 {
 constexpr int kG2P2GThreads = 192;  // 64 cells x 3 stencil slices in phase 2
 constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
 
+struct G2P2GModel {
+	PBuf cur, next;
+	Mat mat;
+};
 struct G2P2GArgs {
 	Cfg cfg;
 	const StepState* state;  // nullable: when set, dt/new_dt/block count come from the device
@@ -41,8 +45,8 @@ struct G2P2GArgs {
 	int block_count;
 	int halo_mode;            // 0: all blocks, 1: only halo-marked, 2: only non-halo (MGSP split, mgsp_benchmark.cuh:421-467)
 	const char* halo_marks;
-	PBuf cur, next;
-	Mat mat;
+	int n_models;             // models of the SAME material handled by one launch: the neighbourhood of a block is staged
+	G2P2GModel m[kMaxModels]; // and written back once for all of them (the reference launches g2p2g once per model, :386-396)
 	const int* prev_table;
 	const int* table;
 	const int* keys;
@@ -75,6 +79,7 @@ struct G2P2GSmem {
 	int cnt[64];
 	int start[65];
 	int nbr[27];
+	int prevno[27];
 	int srcbin[27];
 	int nmovers;
 	unsigned long long bar;
@@ -91,7 +96,7 @@ __device__ __forceinline__ void bspline_poly(int i, float& a, float& b, float& c
 }
 
 template<int MAT>
-__global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a) {
+__global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs a) {
 	constexpr int BINF = (MAT == CB200_J_FLUID) ? 128 : 512;
 	constexpr int T = kG2P2GThreads;
 	constexpr int ITERS = (kChunk + T - 1) / T;
@@ -119,11 +124,11 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 	unsigned phase = 0;
 	const float dx = cfg.dx, dx_inv = cfg.dx_inv, d_inv = cfg.d_inv;
 	const int ppb_mask = cfg.ppb - 1;
-	const float mass = a.mat.mass;
 
 	for(int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-		const int bucket_size = a.next.particle_bucket_sizes[blk];
-		if(bucket_size == 0) continue;
+		int total_size = 0;
+		for(int mi = 0; mi < a.n_models; ++mi) total_size += a.m[mi].next.particle_bucket_sizes[blk];
+		if(total_size == 0) continue;
 		if(a.halo_mode) {
 			const bool is_halo = a.halo_marks[blk] != 0;
 			if((a.halo_mode == 1) != is_halo) continue;
@@ -148,8 +153,7 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 			const int d = tid - 32;
 			const int ox = d / 9 - 1, oy = (d / 3) % 3 - 1, oz = d % 3 - 1;
 			sm.nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
-			const int pno = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
-			sm.srcbin[d] = pno >= 0 ? a.cur.bin_offsets[pno] : -1;
+			sm.prevno[d] = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
 		}
 		{
 			float4* acc4 = reinterpret_cast<float4*>(sm.acc);
@@ -166,8 +170,18 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 		}
 		__syncthreads();
 
-		const int dst_bin0 = a.next.bin_offsets[blk];
-		const int* __restrict__ bucket = a.next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
+		for(int mi = 0; mi < a.n_models; ++mi) {
+		const G2P2GModel& M = a.m[mi];
+		const int bucket_size = M.next.particle_bucket_sizes[blk];
+		if(bucket_size == 0) continue;
+		if(tid < 27) {
+			const int pno = sm.prevno[tid];
+			sm.srcbin[tid] = pno >= 0 ? M.cur.bin_offsets[pno] : -1;
+		}
+		__syncthreads();
+		const float mass = M.mat.mass;
+		const int dst_bin0 = M.next.bin_offsets[blk];
+		const int* __restrict__ bucket = M.next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
 
 		for(int c0 = 0; c0 < bucket_size; c0 += kChunk) {
 			const int nchunk = min(kChunk, bucket_size - c0);
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 				const int dir = advect >> cfg.ppb_shift;
 				const int src_pidib = advect & ppb_mask;
 				const int sbin0 = sm.srcbin[dir];
-				const float* __restrict__ sbin = a.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
+				const float* __restrict__ sbin = M.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
 
 				float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
 				int base[3], ab[3];
@@ -197,49 +211,64 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 					ab[d] = ((base[d] - 1) & 3) + 1;
 				}
 				// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d])
+				// sum-factorised over the separable weights: 288 FMA instead of 27 x 16 operations
 				float vel[3] = {0.f, 0.f, 0.f};
 				float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 				const int nbase = (ab[0] * 8 + ab[1]) * 8 + ab[2];
+				float wxx[3], wyx[3], wzx[3];
 #pragma unroll
 				for(int i = 0; i < 3; ++i) {
-					const float xx = i * dx - lp[0];
+					wxx[i] = w[0][i] * (i * dx - lp[0]);
+					wyx[i] = w[1][i] * (i * dx - lp[1]);
+					wzx[i] = w[2][i] * (i * dx - lp[2]);
+				}
+#pragma unroll
+				for(int i = 0; i < 3; ++i) {
+					float R0 = 0.f, R1 = 0.f, R2 = 0.f, Y0 = 0.f, Y1 = 0.f, Y2 = 0.f, Z0 = 0.f, Z1 = 0.f, Z2 = 0.f;
 #pragma unroll
 					for(int j = 0; j < 3; ++j) {
-						const float xy = j * dx - lp[1];
-						const float wij = w[0][i] * w[1][j];
-#pragma unroll
-						for(int k = 0; k < 3; ++k) {
-							const float xz = k * dx - lp[2];
-							const float W = wij * w[2][k];
-							const float4 v = sm.vel4[nbase + i * 64 + j * 8 + k];
-							const float wv0 = W * v.x, wv1 = W * v.y, wv2 = W * v.z;
-							vel[0] += wv0;
-							vel[1] += wv1;
-							vel[2] += wv2;
-							A[0] += wv0 * xx;
-							A[1] += wv1 * xx;
-							A[2] += wv2 * xx;
-							A[3] += wv0 * xy;
-							A[4] += wv1 * xy;
-							A[5] += wv2 * xy;
-							A[6] += wv0 * xz;
-							A[7] += wv1 * xz;
-							A[8] += wv2 * xz;
-						}
+						const float4 v0 = sm.vel4[nbase + i * 64 + j * 8], v1 = sm.vel4[nbase + i * 64 + j * 8 + 1], v2 = sm.vel4[nbase + i * 64 + j * 8 + 2];
+						const float P0 = w[2][0] * v0.x + w[2][1] * v1.x + w[2][2] * v2.x;
+						const float P1 = w[2][0] * v0.y + w[2][1] * v1.y + w[2][2] * v2.y;
+						const float P2 = w[2][0] * v0.z + w[2][1] * v1.z + w[2][2] * v2.z;
+						const float Q0 = wzx[0] * v0.x + wzx[1] * v1.x + wzx[2] * v2.x;
+						const float Q1 = wzx[0] * v0.y + wzx[1] * v1.y + wzx[2] * v2.y;
+						const float Q2 = wzx[0] * v0.z + wzx[1] * v1.z + wzx[2] * v2.z;
+						R0 += w[1][j] * P0;
+						R1 += w[1][j] * P1;
+						R2 += w[1][j] * P2;
+						Y0 += wyx[j] * P0;
+						Y1 += wyx[j] * P1;
+						Y2 += wyx[j] * P2;
+						Z0 += w[1][j] * Q0;
+						Z1 += w[1][j] * Q1;
+						Z2 += w[1][j] * Q2;
 					}
+					vel[0] += w[0][i] * R0;
+					vel[1] += w[0][i] * R1;
+					vel[2] += w[0][i] * R2;
+					A[0] += wxx[i] * R0;
+					A[1] += wxx[i] * R1;
+					A[2] += wxx[i] * R2;
+					A[3] += w[0][i] * Y0;
+					A[4] += w[0][i] * Y1;
+					A[5] += w[0][i] * Y2;
+					A[6] += w[0][i] * Z0;
+					A[7] += w[0][i] * Z1;
+					A[8] += w[0][i] * Z2;
 				}
 #pragma unroll
 				for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
 
 				float contrib[9];
-				float* __restrict__ dbin = a.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
+				float* __restrict__ dbin = M.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
 				if constexpr(MAT == CB200_J_FLUID) {
 					float J = __ldg(sbin + 96);
 					J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
 					if(J < 0.1f) J = 0.1f;
-					const float voln = J * a.mat.volume;
-					const float pressure = a.mat.bulk * (powf(J, -a.mat.gamma) - 1.f);
-					const float vs = d_inv * a.mat.viscosity;
+					const float voln = J * M.mat.volume;
+					const float pressure = M.mat.bulk * (powf(J, -M.mat.gamma) - 1.f);
+					const float vs = d_inv * M.mat.viscosity;
 					contrib[0] = ((A[0] + A[0]) * vs - pressure) * voln;
 					contrib[1] = (A[1] + A[3]) * vs * voln;
 					contrib[2] = (A[2] + A[6]) * vs * voln;
@@ -270,11 +299,11 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 					if constexpr(MAT == CB200_FIXED_COROTATED) {
 #pragma unroll
 						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
-						stress_fixed_corotated(a.mat, F, contrib);
+						stress_fixed_corotated_polar(M.mat, F, contrib);
 					} else {
 						float log_jp = __ldg(sbin + 12 * 32);
-						if constexpr(MAT == CB200_SAND) stress_sand(a.mat, F, contrib, log_jp);
-						else stress_nacc(a.mat, F, contrib, log_jp);
+						if constexpr(MAT == CB200_SAND) stress_sand(M.mat, F, contrib, log_jp);
+						else stress_nacc(M.mat, F, contrib, log_jp);
 #pragma unroll
 						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
 						dbin[12 * 32] = log_jp;
@@ -302,13 +331,13 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 					if(bno >= 0) {
 						const int dirtag = (1 - rel[0]) * 9 + (1 - rel[1]) * 3 + (1 - rel[2]);
 						const int cellno = ((cell[0] & 3) << 4) | ((cell[1] & 3) << 2) | (cell[2] & 3);
-						int* cnt = a.next.cell_particle_counts + (size_t) bno * kBlockVol + cellno;
+						int* cnt = M.next.cell_particle_counts + (size_t) bno * kBlockVol + cellno;
 						const int s = atomicAdd(cnt, 1);
 						if(s >= cfg.max_ppc) {
 							atomicSub(cnt, 1);
 							if(a.error) atomicOr(a.error, kErrCellOverflow);
 						} else {
-							a.next.cellbuckets[((size_t) bno << cfg.ppb_shift) + (cellno << cfg.ppc_shift) + s] = (dirtag << cfg.ppb_shift) | pidib;
+							M.next.cellbuckets[((size_t) bno << cfg.ppb_shift) + (cellno << cfg.ppc_shift) + s] = (dirtag << cfg.ppb_shift) | pidib;
 						}
 					} else if(a.error) {
 						atomicOr(a.error, kErrLostParticle);
@@ -450,6 +479,7 @@ __global__ void __launch_bounds__(kG2P2GThreads) g2p2g_kernel(const G2P2GArgs a)
 			if(tid == 64) sm.nmovers = 0;
 			__syncthreads();
 		}
+		}  // models
 
 		// ---- arena -> next grid: eight 1-KiB bulk add-reductions ----------------------------------
 		fence_proxy_async();

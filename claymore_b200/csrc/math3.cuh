@@ -226,6 +226,63 @@ __device__ __forceinline__ void stress_fixed_corotated(const Mat& m, const float
 	p_ft_vol(PF, P, F, m.volume);
 }
 
+// FIXED_COROTATED without the SVD.  With the polar decomposition F = R S:
+//   P F^T = 2 mu (F - R) F^T + lambda (J - 1) J I          (identical to U P_hat V^T F^T of the reference)
+// R is obtained by Newton's iteration R <- (R + R^-T) / 2 (quadratically convergent; 3-4 iterations for the stretches
+// an elastic body sees), which costs ~1/4 of the Jacobi SVD + QR.  Inverted or nearly singular F (det <= 1e-6), where the
+// reference's SVD convention (proper rotations, negative last singular value) matters, takes the SVD path.
+__device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const float* F, float* PF) {
+	float R[9];
+#pragma unroll
+	for(int i = 0; i < 9; ++i) R[i] = F[i];
+	float J = 1.f;
+	bool ok = true;
+#pragma unroll 1
+	for(int it = 0; it < 12; ++it) {
+		float C[9];  // cofactor matrix (column-major): R^-T = C / det
+		C[0] = R[4] * R[8] - R[7] * R[5];
+		C[1] = R[6] * R[5] - R[3] * R[8];
+		C[2] = R[3] * R[7] - R[6] * R[4];
+		C[3] = R[7] * R[2] - R[1] * R[8];
+		C[4] = R[0] * R[8] - R[6] * R[2];
+		C[5] = R[6] * R[1] - R[0] * R[7];
+		C[6] = R[1] * R[5] - R[4] * R[2];
+		C[7] = R[3] * R[2] - R[0] * R[5];
+		C[8] = R[0] * R[4] - R[3] * R[1];
+		const float det = R[0] * C[0] + R[3] * C[3] + R[6] * C[6];
+		if(it == 0) {
+			J = det;
+			if(det <= 1e-6f) {
+				ok = false;
+				break;
+			}
+		}
+		const float h = __fdividef(0.5f, det);
+		float d2 = 0.f;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) {
+			const float r = fmaf(h, C[i], 0.5f * R[i]);
+			const float d = r - R[i];
+			d2 = fmaf(d, d, d2);
+			R[i] = r;
+		}
+		if(d2 < 1e-13f) break;
+	}
+	if(!ok) {
+		stress_fixed_corotated(m, F, PF);
+		return;
+	}
+	float D[9];
+#pragma unroll
+	for(int i = 0; i < 9; ++i) D[i] = F[i] - R[i];
+	const float mu2v = 2.f * m.mu * m.volume;
+	const float iso = m.lambda * (J - 1.f) * J * m.volume;
+#pragma unroll
+	for(int c = 0; c < 3; ++c)
+#pragma unroll
+		for(int r = 0; r < 3; ++r) PF[r + 3 * c] = mu2v * (D[r] * F[c] + D[r + 3] * F[c + 3] + D[r + 6] * F[c + 6]) + ((r == c) ? iso : 0.f);
+}
+
 // SAND: Drucker-Prager return mapping on the Hencky strain, StVK-Hencky elasticity; F and log_jp are updated
 __device__ __forceinline__ void stress_sand(const Mat& m, float* F, float* PF, float& log_jp) {
 	float U[9], S[3], V[9];
