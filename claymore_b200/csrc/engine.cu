@@ -258,7 +258,7 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 			a.dst_buckets[m] = s->models[m].pb[R].blockbuckets;
 			a.bin_sizes[m] = s->models[m].bin_sizes;
 		}
-		rebuild_kernel<<<grid_blocks(8), kBucketThreads, 0, st>>>(a);
+		rebuild_kernel<<<grid_blocks(16), kBucketThreads, 0, st>>>(a);
 		++s->launches;
 	}
 	for(int m = 0; m < nm; ++m) {

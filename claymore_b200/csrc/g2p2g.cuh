@@ -201,6 +201,15 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 				const float* __restrict__ sbin = M.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
 
 				float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
+				// the remaining channels are needed only after G2P: pull their lines into L1 now (no registers held)
+				if constexpr(MAT == CB200_J_FLUID) {
+					prefetch_l1(sbin + 96);
+				} else {
+#pragma unroll
+					for(int d = 0; d < 9; ++d) prefetch_l1(sbin + (3 + d) * 32);
+					if constexpr(MAT != CB200_FIXED_COROTATED) prefetch_l1(sbin + 12 * 32);
+				}
+				if(slot + T < nchunk) prefetch_l1(bucket + pidib + T);
 				int base[3], ab[3];
 				float lp[3], w[3][3];
 #pragma unroll
@@ -260,6 +269,36 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 #pragma unroll
 				for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
 
+				// ---- re-bucket (add_advection), part 1: claim a slot in the new cell NOW so that the round trip of the
+				// global atomic overlaps the deformation-gradient / stress arithmetic below; the tag is stored after it
+				int nb[3], cell[3];
+				int rb_slot = -1, rb_tag = 0;
+				size_t rb_cell = 0;
+				{
+					int rel[3];
+					bool far = false;
+#pragma unroll
+					for(int d = 0; d < 3; ++d) {
+						nb[d] = cell_index(cfg, pos[d]) - 1;
+						cell[d] = nb[d] - 1;
+					}
+					rel[0] = (cell[0] >> 2) - kx;
+					rel[1] = (cell[1] >> 2) - ky;
+					rel[2] = (cell[2] >> 2) - kz;
+#pragma unroll
+					for(int d = 0; d < 3; ++d) far |= (rel[d] < -1) | (rel[d] > 1);
+					const int bno = far ? -1 : sm.nbr[(rel[0] + 1) * 9 + (rel[1] + 1) * 3 + rel[2] + 1];
+					if(bno >= 0) {
+						const int dirtag = (1 - rel[0]) * 9 + (1 - rel[1]) * 3 + (1 - rel[2]);
+						const int cellno = ((cell[0] & 3) << 4) | ((cell[1] & 3) << 2) | (cell[2] & 3);
+						rb_cell = (size_t) bno * kBlockVol + cellno;
+						rb_tag = (dirtag << cfg.ppb_shift) | pidib;
+						rb_slot = atomicAdd(M.next.cell_particle_counts + rb_cell, 1);
+					} else if(a.error) {
+						atomicOr(a.error, kErrLostParticle);
+					}
+				}
+
 				float contrib[9];
 				float* __restrict__ dbin = M.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
 				if constexpr(MAT == CB200_J_FLUID) {
@@ -312,38 +351,17 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 #pragma unroll
 				for(int d = 0; d < 9; ++d) contrib[d] = (A[d] * mass - contrib[d] * new_dt) * d_inv;
 
-				// ---- re-bucket (add_advection) ---------------------------------------------------
-				int nb[3], rel[3], cell[3];
-				bool far = false;
+				// ---- re-bucket, part 2: store the advection tag into the claimed slot --------------------
 #pragma unroll
-				for(int d = 0; d < 3; ++d) {
-					nb[d] = cell_index(cfg, pos[d]) - 1;
-					lp[d] = pos[d] - nb[d] * dx;
-					cell[d] = nb[d] - 1;
-				}
-				rel[0] = (cell[0] >> 2) - kx;
-				rel[1] = (cell[1] >> 2) - ky;
-				rel[2] = (cell[2] >> 2) - kz;
-#pragma unroll
-				for(int d = 0; d < 3; ++d) far |= (rel[d] < -1) | (rel[d] > 1);
-				if(!far) {
-					const int bno = sm.nbr[(rel[0] + 1) * 9 + (rel[1] + 1) * 3 + rel[2] + 1];
-					if(bno >= 0) {
-						const int dirtag = (1 - rel[0]) * 9 + (1 - rel[1]) * 3 + (1 - rel[2]);
-						const int cellno = ((cell[0] & 3) << 4) | ((cell[1] & 3) << 2) | (cell[2] & 3);
-						int* cnt = M.next.cell_particle_counts + (size_t) bno * kBlockVol + cellno;
-						const int s = atomicAdd(cnt, 1);
-						if(s >= cfg.max_ppc) {
-							atomicSub(cnt, 1);
-							if(a.error) atomicOr(a.error, kErrCellOverflow);
-						} else {
-							M.next.cellbuckets[((size_t) bno << cfg.ppb_shift) + (cellno << cfg.ppc_shift) + s] = (dirtag << cfg.ppb_shift) | pidib;
-						}
-					} else if(a.error) {
-						atomicOr(a.error, kErrLostParticle);
+				for(int d = 0; d < 3; ++d) lp[d] = pos[d] - nb[d] * dx;
+				if(rb_slot >= 0) {
+					if(rb_slot >= cfg.max_ppc) {
+						atomicSub(M.next.cell_particle_counts + rb_cell, 1);
+						if(a.error) atomicOr(a.error, kErrCellOverflow);
+					} else {
+						// cellbuckets index = block * ppb + cell * max_ppc + slot == (block*64 + cell) * max_ppc + slot
+						M.next.cellbuckets[(rb_cell << cfg.ppc_shift) + rb_slot] = rb_tag;
 					}
-				} else if(a.error) {
-					atomicOr(a.error, kErrLostParticle);
 				}
 
 				// ---- stage the P2G record ----------------------------------------------------------
