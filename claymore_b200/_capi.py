@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libclaymore_b200.so")
+_VARIANT = os.environ.get("CB200_LIB_VARIANT", "")   # experiment builds only (csrc/Makefile `variants`)
+_LIB = os.path.join(_HERE, "lib", f"libclaymore_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 
 J_FLUID, FIXED_COROTATED, SAND, NACC = 0, 1, 2, 3
 CHANNELS = {J_FLUID: 4, FIXED_COROTATED: 12, SAND: 13, NACC: 13}

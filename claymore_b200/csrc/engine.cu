@@ -258,17 +258,20 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 			a.dst_buckets[m] = s->models[m].pb[R].blockbuckets;
 			a.bin_sizes[m] = s->models[m].bin_sizes;
 		}
-		rebuild_kernel<<<grid_blocks(16), kBucketThreads, 0, st>>>(a);
+		rebuild_kernel<<<grid_blocks(8), 256, 0, st>>>(a);
 		++s->launches;
 	}
-	for(int m = 0; m < nm; ++m) {
-		ScanArgs a {};
-		a.count = count_dev(s->d_scratch + 0);
-		a.count_plus = 1;
-		a.in = s->models[m].bin_sizes;
-		a.out = s->models[m].pb[R].bin_offsets;
-		a.total_out = &s->d_state->bin_count[m];
-		scan_kernel<<<1, 1024, 0, st>>>(a);
+	{
+		ScanBatch b {};
+		for(int m = 0; m < nm; ++m) {
+			ScanArgs& a = b.a[m];
+			a.count = count_dev(s->d_scratch + 0);
+			a.count_plus = 1;
+			a.in = s->models[m].bin_sizes;
+			a.out = s->models[m].pb[R].bin_offsets;
+			a.total_out = &s->d_state->bin_count[m];
+		}
+		scan_batch_kernel<<<nm, 1024, 0, st>>>(b);
 		++s->launches;
 	}
 	{
@@ -413,6 +416,7 @@ void preload_kernels() {
 	preload(clear_grid_kernel);
 	preload(carry_grid_kernel);
 	preload(scan_kernel);
+	preload(scan_batch_kernel);
 	preload(block_summary_kernel);
 	preload(rebuild_kernel);
 	preload(register_blocks_kernel);

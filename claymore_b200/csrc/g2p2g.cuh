@@ -31,7 +31,14 @@
 
 namespace cb200 {
 
-constexpr int kG2P2GThreads = 192;  // 64 cells x 3 stencil slices in phase 2
+#ifndef CB200_G2P2G_THREADS
+#define CB200_G2P2G_THREADS 192
+#endif
+#ifndef CB200_G2P2G_MIN_CTAS
+#define CB200_G2P2G_MIN_CTAS 4  // measured on B200 (5M / 40M spheres): 2 CTAs/SM 6.4 / 7.0, 3: 7.7 / 8.5, 4: 8.4 / 9.3 G particle-steps/s;
+#endif                          // the kernel is latency bound (issue slots ~45 % busy), warps in flight beat spill-free registers
+constexpr int kG2P2GThreads = CB200_G2P2G_THREADS;  // >= 192 = 64 cells x 3 stencil slices in phase 2
+static_assert(kG2P2GThreads >= 192 && kG2P2GThreads % 32 == 0, "phase 2 maps one thread to (cell, slice)");
 constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
 
 struct G2P2GModel {
@@ -72,8 +79,8 @@ __device__ __forceinline__ int acc_off_z(int Z) { return (Z >> 2) * 256 + (Z & 3
 struct G2P2GSmem {
 	float4 vel4[512];                // node-major velocity arena, index (X*8+Y)*8+Z
 	float acc[8 * 256];              // accumulation arena (grid-block layout)
-	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads
-	float velsoa[8 * 192];           // TMA landing zone: 8 blocks x 3 channels x 64 cells
+	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads; its first 6 KiB double as the TMA landing
+	                                 // zone (8 blocks x 3 channels x 64 cells) while a block's neighbourhood is staged
 	unsigned short idx[kChunk];      // staged slots sorted by cell
 	unsigned short movers[kChunk];   // staged slots of particles that changed cell
 	int cnt[64];
@@ -96,7 +103,7 @@ __device__ __forceinline__ void bspline_poly(int i, float& a, float& b, float& c
 }
 
 template<int MAT>
-__global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs a) {
+__global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_kernel(const G2P2GArgs a) {
 	constexpr int BINF = (MAT == CB200_J_FLUID) ? 128 : 512;
 	constexpr int T = kG2P2GThreads;
 	constexpr int ITERS = (kChunk + T - 1) / T;
@@ -104,6 +111,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	G2P2GSmem& sm = *reinterpret_cast<G2P2GSmem*>(smem_raw);
 	uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar);
+	float* const velsoa = reinterpret_cast<float*>(&sm.rec[0][0]);  // consumed (transposed into vel4) before any record is staged
 
 	const Cfg& cfg = a.cfg;
 	const int tid = threadIdx.x;
@@ -144,9 +152,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 			__syncwarp();
 			if(tid < 8) {
 				if(bno >= 0) {
-					tma_load_1d(sm.velsoa + lb * 192, a.grid + (size_t) bno * kGridBlockFloats + 64, 768, bar);
+					tma_load_1d(velsoa + lb * 192, a.grid + (size_t) bno * kGridBlockFloats + 64, 768, bar);
 				} else {
-					for(int i = 0; i < 192; ++i) sm.velsoa[lb * 192 + i] = 0.f;
+					for(int i = 0; i < 192; ++i) velsoa[lb * 192 + i] = 0.f;
 				}
 			}
 		} else if(tid < 32 + 27) {
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 		for(int n = tid; n < 512; n += T) {
 			const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
 			const int o = (((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2)) * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
-			sm.vel4[n] = make_float4(sm.velsoa[o], sm.velsoa[o + 64], sm.velsoa[o + 128], 0.f);
+			sm.vel4[n] = make_float4(velsoa[o], velsoa[o + 64], velsoa[o + 128], 0.f);
 		}
 		__syncthreads();
 
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, 3) g2p2g_kernel(const G2P2GArgs
 			__syncthreads();
 
 			// ================= phase 2: cell-parallel accumulation =====================================
-			{
+			if(tid < 192) {
 				const int hc = tid / 3, sl = tid - 3 * hc;
 				const int n = sm.cnt[hc], st = sm.start[hc];
 				float pa, pb, pc;

@@ -40,7 +40,8 @@ struct ScanArgs {
 	int* error;
 	int error_bit;
 };
-__global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) {
+constexpr int kScanPer = 8;  // elements per thread per pass (8192 per CTA pass)
+__device__ __forceinline__ void scan_body(const ScanArgs& a) {
 	__shared__ int s_warp[32];
 	__shared__ int s_carry;
 	const int n = a.count.get();
@@ -48,12 +49,15 @@ __global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if(tid == 0) s_carry = 0;
 	__syncthreads();
-	for(int base = 0; base < n_out; base += 4096) {
-		const int i0 = base + tid * 4;
-		int v[4];
+	for(int base = 0; base < n_out; base += 1024 * kScanPer) {
+		const int i0 = base + tid * kScanPer;
+		int v[kScanPer];
+		int tsum = 0;
 #pragma unroll
-		for(int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? a.in[i0 + k] : 0;
-		const int tsum = v[0] + v[1] + v[2] + v[3];
+		for(int k = 0; k < kScanPer; ++k) {
+			v[k] = (i0 + k < n) ? a.in[i0 + k] : 0;
+			tsum += v[k];
+		}
 		int inc = tsum;
 #pragma unroll
 		for(int o = 1; o < 32; o <<= 1) {
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) {
 		const int carry = s_carry;
 		int ex = carry + (warp ? s_warp[warp - 1] : 0) + inc - tsum;
 #pragma unroll
-		for(int k = 0; k < 4; ++k) {
+		for(int k = 0; k < kScanPer; ++k) {
 			if(i0 + k < n_out) a.out[i0 + k] = ex;
 			ex += v[k];
 		}
@@ -93,6 +97,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) {
 		if(a.total_out2) *a.total_out2 = total;
 	}
 }
+__global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) { scan_body(a); }
+// several independent scans in one launch (one CTA each): the per-model bin-offset scans of a sub-step
+struct ScanBatch {
+	ScanArgs a[kMaxModels];
+};
+__global__ void __launch_bounds__(1024) scan_batch_kernel(const ScanBatch b) { scan_body(b.a[blockIdx.x]); }
 
 // exclusive_scan_inverse (Library/MnBase/Algorithm/MappingKernels.cuh:44-55)
 __global__ void scan_inverse_kernel(int num, const int* map, int* map_inv) {
@@ -205,14 +215,48 @@ struct RebuildArgs {
 	int* dst_buckets[kMaxModels];
 	int* bin_sizes[kMaxModels];
 };
-__global__ void __launch_bounds__(kBucketThreads) rebuild_kernel(const RebuildArgs a) {
-	__shared__ int s_prefix[65];
+// one WARP per old block: the 64 cell counts are prefix-summed with shuffles, a tag finds its cell by a 6-step binary
+// search over the lane-distributed prefix (shuffles, no shared memory, no block barrier), so the eight warps of a CTA
+// stream independent blocks and hide each other's latency.
+__device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst) {
+	const int lane = threadIdx.x & 31;
+	const int2 c = reinterpret_cast<const int2*>(cell_counts_blk)[lane];
+	const int pair = c.x + c.y;
+	int inc = pair;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, inc, o);
+		if(lane >= o) inc += t;
+	}
+	const int p_even = inc - pair;       // exclusive prefix of cell 2*lane
+	const int p_odd = p_even + c.x;      // exclusive prefix of cell 2*lane + 1
+	const int total = __shfl_sync(0xffffffffu, inc, 31);
+	for(int i0 = 0; i0 < total; i0 += 32) {
+		const int i = i0 + lane;
+		// largest lane L with p_even(L) <= i
+		int L = 0;
+#pragma unroll
+		for(int s = 16; s > 0; s >>= 1) {
+			const int probe = __shfl_sync(0xffffffffu, p_even, (L + s) & 31);
+			if(probe <= i) L += s;
+		}
+		const int pe = __shfl_sync(0xffffffffu, p_even, L);
+		const int po = __shfl_sync(0xffffffffu, p_odd, L);
+		const bool odd = po <= i;
+		const int cell = 2 * L + (odd ? 1 : 0);
+		const int off = i - (odd ? po : pe);
+		if(i < total) dst[i] = cellbuckets_blk[(cell << cfg.ppc_shift) + off];
+	}
+	return total;
+}
+__global__ void __launch_bounds__(256) rebuild_kernel(const RebuildArgs a) {
 	const Cfg& cfg = a.cfg;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int ebc = a.state->ebc;
-	for(int b = blockIdx.x; b < ebc; b += gridDim.x) {
+	for(int b = blockIdx.x * 8 + warp; b < ebc; b += gridDim.x * 8) {
 		if(!a.marks[b]) continue;
 		const int nb = a.dest[b];
-		if(threadIdx.x == 0) {
+		if(lane == 0) {
 			const int x = a.old_keys[3 * b], y = a.old_keys[3 * b + 1], z = a.old_keys[3 * b + 2];
 			a.new_keys[3 * nb] = x;
 			a.new_keys[3 * nb + 1] = y;
@@ -220,8 +264,8 @@ __global__ void __launch_bounds__(kBucketThreads) rebuild_kernel(const RebuildAr
 			a.new_table[table_offset(cfg, x, y, z)] = nb;
 		}
 		for(int m = 0; m < a.n_models; ++m) {
-			const int total = flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift), s_prefix);
-			if(threadIdx.x == 0) {
+			const int total = warp_flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift));
+			if(lane == 0) {
 				a.dst_sizes[m][nb] = total;
 				a.bin_sizes[m][nb] = (total + kBinCap - 1) / kBinCap;
 			}
