@@ -164,6 +164,7 @@ def run_reference(args):
 
 
 def run_b200(args):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     import torch.distributed as dist
     import scenes

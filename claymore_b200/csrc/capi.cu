@@ -98,6 +98,9 @@ int cb200_g2p2g(const cb200_config* c, float dt, float new_dt, int pbc, cb200_pa
 	a.grid = grid;
 	a.next_grid = next_grid;
 	a.error = nullptr;
+	a.work_counter = nullptr;
+	a.block_list = nullptr;
+	a.list_count = nullptr;
 	return (int) launch_g2p2g(cur.material, a, pbc, (cudaStream_t) stream);
 }
 

@@ -95,14 +95,23 @@ struct cb200_sim {
 	unsigned char* inbox_peer[kMaxRanks] = {};
 	bool inbox_opened[kMaxRanks] = {};
 	bool peers_ready = false;
+	int* halo_list[2] = {nullptr, nullptr};      // per partition: block numbers of halo / interior particle blocks
+	int* interior_list[2] = {nullptr, nullptr};
+	int* interior_count[2] = {nullptr, nullptr};
 	int* mgsp_done = nullptr;    // [4] last-CTA counters
 	int* mgsp_epochs = nullptr;  // [3]
 	// per-kernel timing (cudaEvent pairs around the g2p2g launches; stream mode only)
 	bool profiling = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 	size_t prof_used = 0;
+	// phase marks (profiling mode only): one event after every phase of a sub-step
+	std::vector<cudaEvent_t> phase_events;
+	std::vector<int> phase_ids;
+	size_t phase_used = 0;
 	bool capturing = false;
 	bool owns_stream = false;
+	cudaStream_t side = nullptr;  // MGSP: halo g2p2g + send run here, concurrently with the interior g2p2g
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -165,6 +174,14 @@ G2P2GArgs make_g2p2g_args(cb200_sim* s, int material, int R, int halo_mode) {
 	a.grid = s->grid[0];
 	a.next_grid = s->grid[1];
 	a.error = &s->d_state->error;
+	a.work_counter = halo_mode == 1 ? &s->d_state->work_counter2 : &s->d_state->work_counter;
+	if(halo_mode == 1) {
+		a.block_list = s->halo_list[R];
+		a.list_count = s->part[R].halo_count;
+	} else if(halo_mode == 2) {
+		a.block_list = s->interior_list[R];
+		a.list_count = s->interior_count[R];
+	}
 	return a;
 }
 
@@ -185,7 +202,14 @@ int enqueue_grid_update(cb200_sim* s, int R) {
 	return (int) cudaGetLastError();
 }
 // ---- phase B: g2p2g --------------------------------------------------------------------------------
-int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode) {
+int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode, cudaStream_t st = nullptr) {
+	if(!st) st = s->stream;
+	int n_materials = 0;
+	for(int material = 0; material < 4; ++material) {
+		bool any = false;
+		for(const Model& m : s->models) any |= m.material == material;
+		n_materials += any;
+	}
 	for(int material = 0; material < 4; ++material) {
 		const G2P2GArgs a = make_g2p2g_args(s, material, R, halo_mode);
 		if(a.n_models == 0) continue;
@@ -197,10 +221,12 @@ int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode) {
 				CK(cudaEventCreate(&e1));
 				s->prof_events.emplace_back(e0, e1);
 			}
-			CK(cudaEventRecord(s->prof_events[s->prof_used].first, s->stream));
+			CK(cudaEventRecord(s->prof_events[s->prof_used].first, st));
 		}
-		CK(launch_g2p2g(material, a, -1, s->stream));
-		if(timed) CK(cudaEventRecord(s->prof_events[s->prof_used++].second, s->stream));
+		G2P2GArgs b = a;
+		if(n_materials > 1) b.work_counter = nullptr;  // one queue per launch: several materials fall back to static striding
+		CK(launch_g2p2g(material, b, -1, st));
+		if(timed) CK(cudaEventRecord(s->prof_events[s->prof_used++].second, st));
 		++s->launches;
 	}
 	return 0;
@@ -365,32 +391,65 @@ int enqueue_halo_reduce(cb200_sim* s, int g, int P) {
 int enqueue_halo_tagging(cb200_sim* s, int P, const int* particle_block_count) {
 	cudaStream_t st = s->stream;
 	const MgspView v = mgsp_view(s);
-	mgsp_tag_reset_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].overlap_marks, s->part[P].count, s->part[P].halo_count);
+	mgsp_tag_reset_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].overlap_marks, s->part[P].count, s->part[P].halo_count, s->interior_count[P]);
 	mgsp_publish_keys_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].active_keys, s->part[P].count);
 	mgsp_tag_kernel<<<grid_blocks(1), 256, 0, st>>>(s->cfg, v, s->part[P].index_table, s->part[P].overlap_marks);
-	collect_halo_blockids_kernel<<<grid_blocks(2), 128, 0, st>>>(s->cfg, count_dev(particle_block_count), s->part[P].index_table, s->part[P].active_keys, s->part[P].overlap_marks, s->part[P].halo_marks, s->part[P].halo_count, nullptr);
+	collect_halo_blockids_kernel<<<grid_blocks(2), 128, 0, st>>>(s->cfg, count_dev(particle_block_count), s->part[P].index_table, s->part[P].active_keys, s->part[P].overlap_marks, s->part[P].halo_marks, s->part[P].halo_count, nullptr, s->halo_list[P], s->interior_list[P], s->interior_count[P]);
 	s->launches += 4;
 	return (int) cudaGetLastError();
 }
 
+// profiling aid: records an event after a phase (ids: 0 start, 1 grid update, 2 max-vel all-reduce, 3 halo g2p2g, 4 halo send,
+// 5 interior g2p2g, 6 halo wait+reduce, 7 rebuild, 8 halo tagging, 9 carry/exterior/finalize)
+int mark_phase(cb200_sim* s, int id) {
+	if(!s->profiling || s->capturing) return 0;
+	if(s->phase_used == s->phase_events.size()) {
+		cudaEvent_t e;
+		CK(cudaEventCreate(&e));
+		s->phase_events.push_back(e);
+		s->phase_ids.push_back(0);
+	}
+	s->phase_ids[s->phase_used] = id;
+	CK(cudaEventRecord(s->phase_events[s->phase_used++], s->stream));
+	return 0;
+}
+
 int enqueue_substep(cb200_sim* s, int R) {
 	int e;
+	mark_phase(s, 0);
 	if((e = enqueue_grid_update(s, R))) return e;
+	mark_phase(s, 1);
 	if(s->desc.mgsp_world > 1) {
 		// dt must be the same on every rank: all-reduce(max) of |v|^2 (host max over devices in the reference, :410-416)
 		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s), &s->d_state->max_vel_sq);
 		++s->launches;
-		if((e = enqueue_g2p2g(s, R, 1))) return e;         // halo particle blocks first            (:421-446)
-		if((e = enqueue_halo_send(s, 1, R))) return e;      // their next-grid blocks go to the peers (:449)
-		if((e = enqueue_g2p2g(s, R, 2))) return e;         // the rest overlaps the transfer         (:451-464)
+		mark_phase(s, 2);
+		// halo particle blocks and their send on the side stream, the other blocks on the main stream: both launches pull
+		// blocks from their own queue and share the SMs; the transfer overlaps whatever is left of the interior launch
+		// (reference: halo g2p2g, barrier, collect+send on spare streams, non-halo g2p2g, barrier; :421-467)
+		CK(cudaEventRecord(s->ev_fork, s->stream));
+		CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+		if((e = enqueue_g2p2g(s, R, 1, s->side))) return e;
+		mgsp_pack_send_kernel<<<grid_blocks(2), 256, 0, s->side>>>(s->cfg, mgsp_view(s), s->grid[1], s->part[R].index_table);
+		++s->launches;
+		CK(cudaEventRecord(s->ev_join, s->side));
+		if((e = enqueue_g2p2g(s, R, 2))) return e;
+		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+		mark_phase(s, 5);
 		if((e = enqueue_halo_reduce(s, 1, R))) return e;    // add what arrived                        (:467)
+		mark_phase(s, 6);
 		if((e = enqueue_rebuild(s, R))) return e;
+		mark_phase(s, 7);
 		if((e = enqueue_halo_tagging(s, R ^ 1, s->d_scratch + 0))) return e;  // (:530)
+		mark_phase(s, 8);
 		if((e = enqueue_carry_and_exterior(s, R))) return e;
+		mark_phase(s, 9);
 		return 0;
 	}
 	if((e = enqueue_g2p2g(s, R, 0))) return e;
+	mark_phase(s, 5);
 	if((e = enqueue_rebuild(s, R))) return e;
+	mark_phase(s, 7);
 	if((e = enqueue_carry_and_exterior(s, R))) return e;
 	return 0;
 }
@@ -498,9 +557,17 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 		CK(cudaMalloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
 		CK(cudaMemsetAsync(s->inbox_local, 0, inbox_bytes(s->inbox_layout), s->stream));
 		s->inbox_peer[s->desc.mgsp_rank] = s->inbox_local;
-		CK(cudaMalloc(&s->mgsp_done, 8 * sizeof(int)));
-		CK(cudaMemsetAsync(s->mgsp_done, 0, 8 * sizeof(int), s->stream));
+		CK(cudaMalloc(&s->mgsp_done, 16 * sizeof(int)));
+		CK(cudaMemsetAsync(s->mgsp_done, 0, 16 * sizeof(int), s->stream));
 		s->mgsp_epochs = s->mgsp_done + 4;
+		for(int i = 0; i < 2; ++i) {
+			CK(cudaMalloc(&s->halo_list[i], (mb + 1) * sizeof(int)));
+			CK(cudaMalloc(&s->interior_list[i], (mb + 1) * sizeof(int)));
+			s->interior_count[i] = s->mgsp_done + 8 + i;
+		}
+		CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	*out = s;
@@ -541,7 +608,14 @@ int cb200_sim_destroy(cb200_sim* s) {
 		if(s->inbox_opened[r]) cudaIpcCloseMemHandle(s->inbox_peer[r]);
 	cudaFree(s->inbox_local);
 	cudaFree(s->mgsp_done);
+	for(int i = 0; i < 2; ++i) {
+		cudaFree(s->halo_list[i]);
+		cudaFree(s->interior_list[i]);
+	}
 	cudaFreeHost(s->h_state);
+	if(s->side) cudaStreamDestroy(s->side);
+	if(s->ev_fork) cudaEventDestroy(s->ev_fork);
+	if(s->ev_join) cudaEventDestroy(s->ev_join);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return 0;
@@ -689,6 +763,9 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 		CK(cudaMemcpyAsync(s->part[R].halo_marks, s->part[Rn].halo_marks, (size_t) pbc, cudaMemcpyDeviceToDevice, st));
 		CK(cudaMemcpyAsync(s->part[R].overlap_marks, s->part[Rn].overlap_marks, (size_t) nbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
 		CK(cudaMemcpyAsync(s->part[R].halo_count, s->part[Rn].halo_count, sizeof(int), cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s->halo_list[R], s->halo_list[Rn], (size_t) pbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s->interior_list[R], s->interior_list[Rn], (size_t) pbc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s->interior_count[R], s->interior_count[Rn], sizeof(int), cudaMemcpyDeviceToDevice, st));
 	}
 	for(Model& m : s->models) {
 		CK(cudaMemcpyAsync(m.pb[Rn].bin_offsets, m.pb[R].bin_offsets, (size_t) (pbc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -905,6 +982,20 @@ int cb200_sim_profile(cb200_sim* s, int enable) {
 	CK(cudaStreamSynchronize(s->stream));
 	s->profiling = enable != 0;
 	s->prof_used = 0;
+	s->phase_used = 0;
+	return 0;
+}
+// summed milliseconds per phase id (see mark_phase) since profiling was enabled; out_ms[10]
+int cb200_sim_profile_phases(cb200_sim* s, double* out_ms) {
+	if(!s || !out_ms) return (int) cudaErrorInvalidValue;
+	CK(cudaStreamSynchronize(s->stream));
+	for(int i = 0; i < 10; ++i) out_ms[i] = 0.0;
+	for(size_t i = 1; i < s->phase_used; ++i) {
+		if(s->phase_ids[i] == 0) continue;  // start of a sub-step: the gap before it belongs to nobody
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, s->phase_events[i - 1], s->phase_events[i]));
+		out_ms[s->phase_ids[i]] += ms;
+	}
 	return 0;
 }
 int cb200_sim_profile_read(cb200_sim* s, double* g2p2g_ms_total, int* launches) {

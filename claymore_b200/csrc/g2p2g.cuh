@@ -60,6 +60,9 @@ struct G2P2GArgs {
 	const float* grid;
 	float* next_grid;
 	int* error;  // nullable
+	int* work_counter;  // nullable: dynamic block queue (device int, zero before the launch); static striding otherwise
+	const int* block_list;  // nullable: compacted list of block numbers to process (MGSP halo / interior lists)
+	const int* list_count;  // its length (device)
 };
 
 // compute_dt (utility_funcs.hpp:36-49) evaluated on the device from the reduced max |v|^2
@@ -89,6 +92,7 @@ struct G2P2GSmem {
 	int prevno[27];
 	int srcbin[27];
 	int nmovers;
+	int next_blk;
 	unsigned long long bar;
 };
 
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		new_dt = device_compute_dt(cfg, a.state->max_vel_sq, a.state->step_time, a.state->frame_time, a.state->dt_default);
 		nblocks = a.state->pbc;
 	}
+	if(a.block_list) nblocks = *a.list_count;
 	if(tid == 0) {
 		mbar_init(bar, 1);
 		mbar_fence_init();
@@ -133,11 +138,20 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 	const float dx = cfg.dx, dx_inv = cfg.dx_inv, d_inv = cfg.d_inv;
 	const int ppb_mask = cfg.ppb - 1;
 
-	for(int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+	// block queue: CTAs pull particle blocks from a device counter, so a launch that shares the SMs with another launch
+	// (MGSP: halo and interior blocks run concurrently on two streams) or starts late still balances
+	if(tid == 0) sm.next_blk = a.work_counter ? atomicAdd(a.work_counter, 1) : (int) blockIdx.x;
+	for(;;) {
+		__syncthreads();
+		const int qi = sm.next_blk;
+		__syncthreads();
+		if(qi >= nblocks) break;
+		if(tid == 0) sm.next_blk = a.work_counter ? atomicAdd(a.work_counter, 1) : qi + (int) gridDim.x;
+		const int blk = a.block_list ? a.block_list[qi] : qi;
 		int total_size = 0;
 		for(int mi = 0; mi < a.n_models; ++mi) total_size += a.m[mi].next.particle_bucket_sizes[blk];
 		if(total_size == 0) continue;
-		if(a.halo_mode) {
+		if(a.halo_mode && !a.block_list) {
 			const bool is_halo = a.halo_marks[blk] != 0;
 			if((a.halo_mode == 1) != is_halo) continue;
 		}

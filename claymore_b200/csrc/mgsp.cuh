@@ -215,11 +215,14 @@ __global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, cons
 }
 
 // reset of the per-step tagging state (reset_overlap_marks / reset_halo_count, hash_table.cuh:60-66)
-__global__ void mgsp_tag_reset_kernel(MgspView v, int* overlap_marks, const int* key_count, int* halo_count) {
+__global__ void mgsp_tag_reset_kernel(MgspView v, int* overlap_marks, const int* key_count, int* halo_count, int* interior_count) {
 	const int n = *key_count;
 	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) overlap_marks[i] = 0;
 	if(blockIdx.x == 0 && (int) threadIdx.x < v.world) v.overlap_count[threadIdx.x] = 0;
-	if(blockIdx.x == 0 && threadIdx.x == 0) *halo_count = 0;
+	if(blockIdx.x == 0 && threadIdx.x == 0) {
+		*halo_count = 0;
+		*interior_count = 0;
+	}
 }
 
 // mark_overlapping_blocks for every peer (halo_kernels.cuh:22-35), keys read from my inbox

@@ -330,6 +330,7 @@ __global__ void finalize_step_kernel(const FinalizeArgs a) {
 	s->step_time += next_dt;
 	s->max_vel_sq = 0.f;
 	s->work_counter = 0;
+	s->work_counter2 = 0;
 	s->steps += 1;
 }
 

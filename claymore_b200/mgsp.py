@@ -99,8 +99,11 @@ def bench_mgsp(args, scene, label, rank, world, local_rank):
     launches = sim.launch_count - l0
     sim.profile(True)
     sim.step(args.steps)
+    phases = sim.profile_phases()
     g_ms, g_n = sim.profile_read()
     sim.profile(False)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {k: round(v / args.steps, 4) for k, v in phases.items()})
     clk = clocks.stop() if rank == 0 else None
     st = sim.stats()
     shared, halo_pb = sim.mgsp_halo_counts()
@@ -141,7 +144,7 @@ def bench_mgsp(args, scene, label, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": label, "particles": n_total, "particles_rank0": n_local, "particle_blocks_rank0": st.particle_block_count, "dt": args.dt,
-                       "halo_blocks_shared_rank0": shared, "halo_particle_blocks_rank0": halo_pb, "l2": "inputs larger than L2", "graph": not args.no_graph,
+                       "halo_blocks_shared_rank0": shared, "halo_particle_blocks_rank0": halo_pb, "l2": "inputs larger than L2", "graph": not args.no_graph, "phase_ms_per_step_by_rank": gathered,
                        "transport": "kernel stores into CUDA-IPC peer inboxes over NVLink (no NCCL on the data path)"},
             "e2e": {"value": n_total * args.steps / e2e_s / 1e6, "unit": "Mparticle-steps/s", "h2d_bytes_per_step": n_local * 12 / args.steps, "d2h_bytes_per_step": n_local * 12 / args.steps + 76},
             "gpu_launches": int(launches), "clocks": clk,

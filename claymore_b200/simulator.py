@@ -167,6 +167,14 @@ class GmpmSimulator:
         check(self.L.cb200_sim_profile_read(self.h, C.byref(ms), C.byref(n)), "profile_read")
         return ms.value, n.value
 
+    PHASES = ("-", "grid_update", "maxvel_allreduce", "halo_g2p2g", "halo_send", "g2p2g", "halo_wait_reduce", "rebuild", "halo_tagging", "carry_exterior_finalize")
+
+    def profile_phases(self):
+        """{phase: summed ms} over the sub-steps issued while profile(True) was on (call before profile_read)."""
+        out = (C.c_double * 10)()
+        check(self.L.cb200_sim_profile_phases(self.h, out), "profile_phases")
+        return {n: out[i] for i, n in enumerate(self.PHASES) if i}
+
     @property
     def launch_count(self):
         return int(self.L.cb200_sim_launch_count(self.h))
