@@ -48,6 +48,14 @@ def workload(name, n_gpus):
         return sc, f"MGSP two elastic spheres (fixed-corotated), {1 << bits}^3 grid, {n_gpus}x5M particles, x-slab static partition"
     if name == "spheres40m":
         return scenes.two_spheres(domain_bits=9), "GMPM two elastic spheres (fixed-corotated), 512^3 grid, 40M particles"
+    if name == "sand20m":
+        return scenes.sand_column(), "GMPM sand column collapse (Drucker-Prager), 512^3 grid, 20M particles"
+    if name == "sand2m":
+        return scenes.sand_column(domain_bits=8, size=(50, 100, 50)), "sand column (Drucker-Prager), 256^3 grid, 2M particles"
+    if name == "fluid40m":
+        return scenes.fluid_dam(), "weakly-compressible fluid dam break, 1024^3 grid, 40M particles"
+    if name == "fluid5m":
+        return scenes.fluid_dam(domain_bits=9, size=(100, 62, 100)), "weakly-compressible fluid dam, 512^3 grid, 5M particles"
     if name == "cube140k":
         return scenes.jelly_cube(), "jelly cube (fixed-corotated), 128^3 grid, 140608 particles"
     if name == "spheres640k":
@@ -233,7 +241,7 @@ def run_b200(args):
     avg_launch_s = g2p2g_ms / max(g2p2g_launches, 1) * 1e-3
     peak, peak_kind = measured_peak_hbm()
     achieved = alg_bytes_per_launch / avg_launch_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "g2p2g_kernel<FIXED_COROTATED>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "g2p2g_kernel<%s>" % {0: "J_FLUID", 1: "FIXED_COROTATED", 2: "SAND", 3: "NACC"}[material], "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                 "launches_timed": g2p2g_launches, "share_of_step": (g2p2g_ms / args.steps) / (ms_total / args.steps)}
     traffic_file = os.path.join(ROOT, "profiles", "g2p2g_traffic.json")

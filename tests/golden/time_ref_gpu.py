@@ -16,7 +16,12 @@ import scenes  # noqa: E402
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "spheres5m"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-    scene = scenes.two_spheres(domain_bits=8 if which == "spheres5m" else 9)
+    if which == "sand20m":
+        scene = scenes.sand_column()
+    elif which == "sand2m":
+        scene = scenes.sand_column(domain_bits=8, size=(50, 100, 50))
+    else:
+        scene = scenes.two_spheres(domain_bits=8 if which == "spheres5m" else 9)
     n = sum(len(m["pos"]) for m in scene["models"])
     sim = rg.build_ref(scene)
     sim.step(5)

@@ -30,6 +30,22 @@ def two_spheres(domain_bits=8, radius=0.1645, centers=((0.30, 0.5, 0.5), (0.70, 
     ])
 
 
+def sand_column(domain_bits=9, size=(100, 250, 100), base_y=8, material=SAND):
+    """Config 3: column of size[0] x size[1] x size[2] cells x 8 particles resting just above the 2-block wall (512^3: 20 M)."""
+    dx = 1.0 / (1 << domain_bits)
+    n = 1 << domain_bits
+    x0, z0 = (n - size[0]) // 2, (n - size[2]) // 2
+    pos = samplers.uniform_box(dx, (x0, base_y, z0), (x0 + size[0], base_y + size[1], z0 + size[2]))
+    return dict(domain_bits=domain_bits, models=[dict(material=material, pos=pos, v0=(0.0, 0.0, 0.0))])
+
+
+def fluid_dam(domain_bits=10, size=(200, 125, 200), base=(16, 16, 16)):
+    """Config 4: weakly-compressible dam of size cells x 8 particles in a corner of the domain (1024^3: 40 M)."""
+    dx = 1.0 / (1 << domain_bits)
+    pos = samplers.uniform_box(dx, base, tuple(b + s for b, s in zip(base, size)))
+    return dict(domain_bits=domain_bits, models=[dict(material=J_FLUID, pos=pos, v0=(0.0, 0.0, 0.0))])
+
+
 def two_cubes_colliding(domain_bits=6, material=FIXED_COROTATED):
     """Two 8^3-cell cubes about to touch (exercises block activation / deactivation and multi-model grids)."""
     dx = 1.0 / (1 << domain_bits)
