@@ -121,6 +121,12 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
+def cpu_threads():
+    """Threads for the CPU legs.  The oracle port stops scaling past 16 threads (measured on the 128-core B200 host with the
+    0.63 M-particle sample: 8 -> 8.6, 16 -> 16.1, 32 -> 14.4, 64 -> 11.2, 128 -> 1.7 M particle-steps/s), so 16 is "all it can use"."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def time_cpu_port(scene, seconds_budget, threads, max_steps=None):
     """The oracle port on the host cores: (particle-steps/s in millions, particles, steps)."""
     import oracle_binding as ob
@@ -148,7 +154,7 @@ def run_reference(args):
         return
     import oracle_binding as ob
     import scenes
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     scene, label = workload("spheres640k", 1)
     n = sum(len(m["pos"]) for m in scene["models"])
     osim = scenes.build_oracle(ob, scene, max_blocks=max_blocks_for(scene), threads=cores)
@@ -283,7 +289,7 @@ def run_b200(args):
     # ---- CPU baseline beside it: the oracle port on the host cores, bounded sample -------------------------------
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         sc, lab = workload("spheres640k", 1)
         v, n_s, steps_s = time_cpu_port(sc, seconds_budget=args.cpu_seconds, threads=cores)
         cpu = {"value": v, "unit": "Mparticle-steps/s", "cores": cores, "kind": "port", "sample": f"{lab}: {n_s} particles x {steps_s} sub-steps (~{args.cpu_seconds:.0f} s), oracle port (OpenMP)"}
