@@ -127,10 +127,10 @@ _SIGNATURES = {
     "cb200_sim_particle_state": [_P, _I, _P, C.POINTER(_I)],
     "cb200_sim_active_keys": [_P, _P, _I, C.POINTER(_I)],
     "cb200_sim_grid": [_P, _P, _I, C.POINTER(_I)],
-    "cb200_sim_mgsp_inbox": [_P, C.POINTER(_P), C.POINTER(C.c_size_t)],
+    "cb200_sim_mgsp_inbox": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t)],
     "cb200_sim_mgsp_ipc_handle": [_P, _P],
     "cb200_sim_mgsp_open_peers": [_P, _P],
-    "cb200_sim_mgsp_set_peers": [_P, C.POINTER(_P)],
+    "cb200_sim_mgsp_set_peers": [_P, C.POINTER(_P), C.POINTER(_P)],
     "cb200_sim_mgsp_halo_counts": [_P, C.POINTER(_I), C.POINTER(_I)],
     "cb200_sim_profile": [_P, _I],
     "cb200_sim_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(_I)],

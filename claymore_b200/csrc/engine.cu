@@ -98,6 +98,9 @@ struct cb200_sim {
 	int* halo_list[2] = {nullptr, nullptr};      // per partition: block numbers of halo / interior particle blocks
 	int* interior_list[2] = {nullptr, nullptr};
 	int* interior_count[2] = {nullptr, nullptr};
+	int* peer_bno = nullptr;                 // [world][max_blocks]
+	float* grid1_peer[kMaxRanks] = {};       // every rank's next grid mapped here (fused remote halo reduction)
+	bool grid1_opened[kMaxRanks] = {};
 	int* mgsp_done = nullptr;    // [4] last-CTA counters
 	int* mgsp_epochs = nullptr;  // [3]
 	// per-kernel timing (cudaEvent pairs around the g2p2g launches; stream mode only)
@@ -175,6 +178,12 @@ G2P2GArgs make_g2p2g_args(cb200_sim* s, int material, int R, int halo_mode) {
 	a.next_grid = s->grid[1];
 	a.error = &s->d_state->error;
 	a.work_counter = halo_mode == 1 ? &s->d_state->work_counter2 : &s->d_state->work_counter;
+	if(s->desc.mgsp_world > 1 && halo_mode == 0) {
+		a.overlap_marks = s->part[R].overlap_marks;
+		a.peer_bno = s->peer_bno;
+		a.peer_stride = s->desc.max_blocks;
+		for(int r = 0; r < s->desc.mgsp_world; ++r) a.peer_grid[r] = s->grid1_peer[r];
+	}
 	if(halo_mode == 1) {
 		a.block_list = s->halo_list[R];
 		a.list_count = s->part[R].halo_count;
@@ -372,6 +381,7 @@ MgspView mgsp_view(cb200_sim* s) {
 	for(int r = 0; r < v.world; ++r) v.inbox[r] = s->inbox_peer[r];
 	v.overlap_keys = s->peer_overlap_keys;
 	v.overlap_count = s->peer_overlap_count;
+	v.peer_bno = s->peer_bno;
 	v.done = s->mgsp_done;
 	v.epochs = s->mgsp_epochs;
 	return v;
@@ -424,19 +434,15 @@ int enqueue_substep(cb200_sim* s, int R) {
 		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s), &s->d_state->max_vel_sq);
 		++s->launches;
 		mark_phase(s, 2);
-		// halo particle blocks and their send on the side stream, the other blocks on the main stream: both launches pull
-		// blocks from their own queue and share the SMs; the transfer overlaps whatever is left of the interior launch
-		// (reference: halo g2p2g, barrier, collect+send on spare streams, non-halo g2p2g, barrier; :421-467)
-		CK(cudaEventRecord(s->ev_fork, s->stream));
-		CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-		if((e = enqueue_g2p2g(s, R, 1, s->side))) return e;
-		mgsp_pack_send_kernel<<<grid_blocks(2), 256, 0, s->side>>>(s->cfg, mgsp_view(s), s->grid[1], s->part[R].index_table);
-		++s->launches;
-		CK(cudaEventRecord(s->ev_join, s->side));
-		if((e = enqueue_g2p2g(s, R, 2))) return e;
-		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+		// ONE g2p2g launch: the arena flush of a block reduces into this rank's next grid and, for grid blocks shared with a
+		// peer, straight into that peer's next grid over NVLink (no pack, no send, no unpack kernels; the reference: halo g2p2g,
+		// barrier, collect_grid_blocks + cudaMemcpyPeerAsync, non-halo g2p2g, barrier, reduce_grid_blocks; :421-467, 723-776).
+		// The max-vel all-reduce above doubles as "every rank has cleared its next grid"; the barrier below as "every remote
+		// reduction has landed".
+		if((e = enqueue_g2p2g(s, R, 0))) return e;
 		mark_phase(s, 5);
-		if((e = enqueue_halo_reduce(s, 1, R))) return e;    // add what arrived                        (:467)
+		mgsp_done_barrier_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s));
+		++s->launches;
 		mark_phase(s, 6);
 		if((e = enqueue_rebuild(s, R))) return e;
 		mark_phase(s, 7);
@@ -496,6 +502,7 @@ void preload_kernels() {
 	preload(mgsp_publish_keys_kernel);
 	preload(mgsp_tag_reset_kernel);
 	preload(mgsp_tag_kernel);
+	preload(mgsp_done_barrier_kernel);
 	g2p2g_prepare_all();
 }
 int ensure_graph(cb200_sim* s, int R) {
@@ -557,6 +564,9 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 		CK(cudaMalloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
 		CK(cudaMemsetAsync(s->inbox_local, 0, inbox_bytes(s->inbox_layout), s->stream));
 		s->inbox_peer[s->desc.mgsp_rank] = s->inbox_local;
+		s->grid1_peer[s->desc.mgsp_rank] = s->grid[1];
+		CK(cudaMalloc(&s->peer_bno, (size_t) s->desc.mgsp_world * mb * sizeof(int)));
+		CK(cudaMemsetAsync(s->peer_bno, 0xff, (size_t) s->desc.mgsp_world * mb * sizeof(int), s->stream));
 		CK(cudaMalloc(&s->mgsp_done, 16 * sizeof(int)));
 		CK(cudaMemsetAsync(s->mgsp_done, 0, 16 * sizeof(int), s->stream));
 		s->mgsp_epochs = s->mgsp_done + 4;
@@ -606,6 +616,9 @@ int cb200_sim_destroy(cb200_sim* s) {
 	cudaFree(s->peer_overlap_count);
 	for(int r = 0; r < kMaxRanks; ++r)
 		if(s->inbox_opened[r]) cudaIpcCloseMemHandle(s->inbox_peer[r]);
+	for(int r = 0; r < kMaxRanks; ++r)
+		if(s->grid1_opened[r]) cudaIpcCloseMemHandle(s->grid1_peer[r]);
+	cudaFree(s->peer_bno);
 	cudaFree(s->inbox_local);
 	cudaFree(s->mgsp_done);
 	for(int i = 0; i < 2; ++i) {
@@ -932,18 +945,22 @@ int cb200_sim_grid(cb200_sim* s, float* grid_host, int capacity_blocks, int* n_o
 long long cb200_sim_launch_count(cb200_sim* s) { return s ? s->launches : 0; }
 
 // ---- MGSP peer wiring ------------------------------------------------------------------------------------------
-int cb200_sim_mgsp_inbox(cb200_sim* s, void** ptr, size_t* bytes) {
+int cb200_sim_mgsp_inbox(cb200_sim* s, void** inbox, void** next_grid, size_t* inbox_bytes_out) {
 	if(!s || s->desc.mgsp_world <= 1) return (int) cudaErrorInvalidValue;
-	if(ptr) *ptr = s->inbox_local;
-	if(bytes) *bytes = inbox_bytes(s->inbox_layout);
+	if(inbox) *inbox = s->inbox_local;
+	if(next_grid) *next_grid = s->grid[1];
+	if(inbox_bytes_out) *inbox_bytes_out = inbox_bytes(s->inbox_layout);
 	return 0;
 }
-int cb200_sim_mgsp_ipc_handle(cb200_sim* s, void* handle64) {
-	if(!s || s->desc.mgsp_world <= 1 || !handle64) return (int) cudaErrorInvalidValue;
+// 128 bytes: cudaIpcMemHandle_t of the inbox, then of the next-grid buffer (target of the peers' fused halo reductions)
+int cb200_sim_mgsp_ipc_handle(cb200_sim* s, void* handle128) {
+	if(!s || s->desc.mgsp_world <= 1 || !handle128) return (int) cudaErrorInvalidValue;
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 	cudaIpcMemHandle_t h;
 	CK(cudaIpcGetMemHandle(&h, s->inbox_local));
-	memcpy(handle64, &h, 64);
+	memcpy(handle128, &h, 64);
+	CK(cudaIpcGetMemHandle(&h, s->grid[1]));
+	memcpy((unsigned char*) handle128 + 64, &h, 64);
 	return 0;
 }
 int cb200_sim_mgsp_open_peers(cb200_sim* s, const void* handles) {
@@ -951,19 +968,26 @@ int cb200_sim_mgsp_open_peers(cb200_sim* s, const void* handles) {
 	for(int r = 0; r < s->desc.mgsp_world; ++r) {
 		if(r == s->desc.mgsp_rank) continue;
 		cudaIpcMemHandle_t h;
-		memcpy(&h, (const unsigned char*) handles + 64 * r, 64);
 		void* p = nullptr;
+		memcpy(&h, (const unsigned char*) handles + 128 * r, 64);
 		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
 		s->inbox_peer[r] = (unsigned char*) p;
 		s->inbox_opened[r] = true;
+		memcpy(&h, (const unsigned char*) handles + 128 * r + 64, 64);
+		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		s->grid1_peer[r] = (float*) p;
+		s->grid1_opened[r] = true;
 	}
 	s->peers_ready = true;
 	return 0;
 }
-int cb200_sim_mgsp_set_peers(cb200_sim* s, void* const* ptrs) {
-	if(!s || s->desc.mgsp_world <= 1 || !ptrs) return (int) cudaErrorInvalidValue;
+int cb200_sim_mgsp_set_peers(cb200_sim* s, void* const* inbox_ptrs, void* const* next_grid_ptrs) {
+	if(!s || s->desc.mgsp_world <= 1 || !inbox_ptrs || !next_grid_ptrs) return (int) cudaErrorInvalidValue;
 	for(int r = 0; r < s->desc.mgsp_world; ++r)
-		if(r != s->desc.mgsp_rank) s->inbox_peer[r] = (unsigned char*) ptrs[r];
+		if(r != s->desc.mgsp_rank) {
+			s->inbox_peer[r] = (unsigned char*) inbox_ptrs[r];
+			s->grid1_peer[r] = (float*) next_grid_ptrs[r];
+		}
 	s->peers_ready = true;
 	return 0;
 }

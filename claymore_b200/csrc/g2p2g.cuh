@@ -63,6 +63,13 @@ struct G2P2GArgs {
 	int* work_counter;  // nullable: dynamic block queue (device int, zero before the launch); static striding otherwise
 	const int* block_list;  // nullable: compacted list of block numbers to process (MGSP halo / interior lists)
 	const int* list_count;  // its length (device)
+	// MGSP fused halo reduction: a grid block that is also active on peer p (bit p of overlap_marks) receives this CTA's
+	// partial sums on BOTH owners: the arena flush issues a second bulk add-reduction straight into the peer's next grid
+	// (CUDA-IPC mapped, NVLink) at the block number the peer gave that key (peer_bno).  nullptr = single-GPU.
+	const int* overlap_marks;
+	const int* peer_bno;     // [world][peer_stride]
+	int peer_stride;
+	float* peer_grid[8];
 };
 
 // compute_dt (utility_funcs.hpp:36-49) evaluated on the device from the reduced max |v|^2
@@ -526,7 +533,18 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		__syncthreads();
 		if(tid < 8) {
 			const int bno = table_query(cfg, a.table, kx + ((tid >> 2) & 1), ky + ((tid >> 1) & 1), kz + (tid & 1));
-			if(bno >= 0) tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
+			if(bno >= 0) {
+				tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
+				if(a.overlap_marks) {
+					unsigned mask = (unsigned) a.overlap_marks[bno];
+					while(mask) {
+						const int p = __ffs(mask) - 1;
+						mask &= mask - 1;
+						const int rb = a.peer_bno[(size_t) p * a.peer_stride + bno];
+						if(rb >= 0) tma_reduce_add_f32(a.peer_grid[p] + (size_t) rb * kGridBlockFloats, sm.acc + tid * 256, 1024);
+					}
+				}
+			}
 			tma_commit();
 			tma_wait_read<0>();
 		}

@@ -58,6 +58,7 @@ struct MgspView {
 	unsigned char* inbox[kMaxRanks];  // inbox of every rank mapped into this process (inbox[rank] is local)
 	int* overlap_keys;                // [world][max_blocks*3]: my blocks that peer p also has
 	int* overlap_count;               // [world]
+	int* peer_bno;                    // [world][max_blocks]: block number of my block b in peer p's partition (-1: not shared)
 	int* done;                        // [4] last-CTA counters
 	int* epochs;                      // device: [0] max-vel, [1] halo, [2] keys
 };
@@ -98,6 +99,25 @@ __global__ void mgsp_allreduce_maxvel_kernel(MgspView v, float* max_vel_sq) {
 		*max_vel_sq = m;
 		v.epochs[0] = epoch;
 	}
+}
+
+// ---- "my remote reductions have landed" barrier: replaces pack / send / reduce in the fused path ---------------------------
+// runs after g2p2g on the same stream (its bulk reductions into the peers' grids are complete at the kernel boundary);
+// publishes an epoch flag to every peer with a system-scope release and waits for everybody's.
+__global__ void mgsp_done_barrier_kernel(MgspView v) {
+	const int epoch = v.epochs[1] + 1, par = epoch & 1;
+	const int t = threadIdx.x;
+	if(t < v.world && t != v.rank) {
+		InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, t, par, v.rank));
+		__threadfence_system();
+		st_release_sys(&h->flag_halo, epoch);
+	}
+	if(t < v.world && t != v.rank) {
+		InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, v.rank, par, t));
+		wait_flag(&h->flag_halo, epoch);
+	}
+	__syncthreads();
+	if(t == 0) v.epochs[1] = epoch;
 }
 
 // ---- halo pack + send (collect_grid_blocks + HaloGridBlocks::send, halo_kernels.cuh:65-80, halo_buffer.cuh:54-59) ---
@@ -217,7 +237,10 @@ __global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, cons
 // reset of the per-step tagging state (reset_overlap_marks / reset_halo_count, hash_table.cuh:60-66)
 __global__ void mgsp_tag_reset_kernel(MgspView v, int* overlap_marks, const int* key_count, int* halo_count, int* interior_count) {
 	const int n = *key_count;
-	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) overlap_marks[i] = 0;
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		overlap_marks[i] = 0;
+		for(int p = 0; p < v.world; ++p) v.peer_bno[(size_t) p * v.L.max_blocks + i] = -1;
+	}
 	if(blockIdx.x == 0 && (int) threadIdx.x < v.world) v.overlap_count[threadIdx.x] = 0;
 	if(blockIdx.x == 0 && threadIdx.x == 0) {
 		*halo_count = 0;
@@ -242,6 +265,7 @@ __global__ void __launch_bounds__(256) mgsp_tag_kernel(Cfg cfg, MgspView v, cons
 			const int bno = table_query(cfg, table, x, y, z);
 			if(bno >= 0) {
 				atomicOr(overlap_marks + bno, 1 << p);
+				v.peer_bno[(size_t) p * v.L.max_blocks + bno] = i;  // the peer's keys arrive in its block order
 				const int h = atomicAdd(&v.overlap_count[p], 1);
 				if(h < v.L.max_blocks) {
 					outk[3 * h] = x;

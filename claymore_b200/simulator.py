@@ -133,24 +133,26 @@ class GmpmSimulator:
 
     # ---- MGSP peer wiring (one process per GPU: exchange the 64-byte IPC handles with any host all-gather) ----------
     def mgsp_ipc_handle(self):
-        buf = (C.c_ubyte * 64)()
+        buf = (C.c_ubyte * 128)()
         check(self.L.cb200_sim_mgsp_ipc_handle(self.h, buf), "mgsp_ipc_handle")
         return bytes(buf)
 
     def mgsp_open_peers(self, handles_by_rank):
         blob = b"".join(handles_by_rank)
-        assert len(blob) == 64 * self.mgsp_world
+        assert len(blob) == 128 * self.mgsp_world
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         check(self.L.cb200_sim_mgsp_open_peers(self.h, buf), "mgsp_open_peers")
 
     def mgsp_inbox(self):
-        p, n = C.c_void_p(), C.c_size_t()
-        check(self.L.cb200_sim_mgsp_inbox(self.h, C.byref(p), C.byref(n)), "mgsp_inbox")
-        return p.value, n.value
+        """(inbox pointer, next-grid pointer) of this rank, for peers living in the same process."""
+        p, g, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(self.L.cb200_sim_mgsp_inbox(self.h, C.byref(p), C.byref(g), C.byref(n)), "mgsp_inbox")
+        return p.value, g.value
 
-    def mgsp_set_peers(self, inbox_ptrs_by_rank):
-        arr = (C.c_void_p * len(inbox_ptrs_by_rank))(*inbox_ptrs_by_rank)
-        check(self.L.cb200_sim_mgsp_set_peers(self.h, arr), "mgsp_set_peers")
+    def mgsp_set_peers(self, ptrs_by_rank):
+        a = (C.c_void_p * len(ptrs_by_rank))(*[p[0] for p in ptrs_by_rank])
+        b = (C.c_void_p * len(ptrs_by_rank))(*[p[1] for p in ptrs_by_rank])
+        check(self.L.cb200_sim_mgsp_set_peers(self.h, a, b), "mgsp_set_peers")
 
     def mgsp_halo_counts(self):
         cnt = (C.c_int * max(self.mgsp_world, 1))()

@@ -197,14 +197,15 @@ CB200_API int cb200_sim_profile_phases(cb200_sim* sim, double* out_ms);
 
 /* MGSP static particle partition, one process per GPU (Projects/MGSP/mgsp_benchmark.cuh:309-559, 661-776).
  * Each rank creates its simulator with mgsp_rank / mgsp_world set and registers ITS OWN particle set with
- * init_model.  Halo grid blocks, the neighbour-key lists for halo tagging and max |v|^2 are exchanged by kernels that
- * store into the peers' inboxes over NVLink (CUDA IPC mapped) and publish epoch flags: the transport needs no host
+ * init_model.  The P2G sums of halo grid blocks are bulk-add-reduced by g2p2g itself straight into the peers' next grids
+ * over NVLink; the neighbour-key lists for halo tagging and max |v|^2 are exchanged by kernels that store into the peers'
+ * inboxes (both CUDA IPC mapped) and publish epoch flags: the transport needs no host
  * calls per sub-step.  Setup: every rank publishes its inbox handle, all ranks open all handles (any host-side
  * all-gather: torch.distributed here), then initial_setup / step run as in the single-GPU case. */
-CB200_API int cb200_sim_mgsp_inbox(cb200_sim* sim, void** ptr, size_t* bytes);
-CB200_API int cb200_sim_mgsp_ipc_handle(cb200_sim* sim, void* handle64);                /* cudaIpcMemHandle_t, 64 bytes */
-CB200_API int cb200_sim_mgsp_open_peers(cb200_sim* sim, const void* handles64_by_rank); /* world x 64 bytes */
-CB200_API int cb200_sim_mgsp_set_peers(cb200_sim* sim, void* const* inbox_ptrs_by_rank); /* same-process peers */
+CB200_API int cb200_sim_mgsp_inbox(cb200_sim* sim, void** inbox, void** next_grid, size_t* inbox_bytes);
+CB200_API int cb200_sim_mgsp_ipc_handle(cb200_sim* sim, void* handle128);                 /* two cudaIpcMemHandle_t: inbox, next grid */
+CB200_API int cb200_sim_mgsp_open_peers(cb200_sim* sim, const void* handles128_by_rank);  /* world x 128 bytes */
+CB200_API int cb200_sim_mgsp_set_peers(cb200_sim* sim, void* const* inbox_ptrs_by_rank, void* const* next_grid_ptrs_by_rank); /* same-process peers */
 /* halo statistics of the current partition (synchronises): blocks shared with each rank, halo particle blocks */
 CB200_API int cb200_sim_mgsp_halo_counts(cb200_sim* sim, int* shared_blocks_by_rank, int* halo_particle_blocks);
 

@@ -236,7 +236,7 @@ def test_mgsp_two_shards_match_single_domain(oracle, cuda_lib):
     for r in range(2):
         part = mgsp.partition_scene(scene, r, 2)
         sims.append(mgsp.build_rank_sim(part, r, 2, 1e-4, 4000, scenes.apply_material))
-    ptrs = [s.mgsp_inbox()[0] for s in sims]
+    ptrs = [s.mgsp_inbox() for s in sims]
     for s in sims:
         s.mgsp_set_peers(ptrs)
     # initial_setup synchronises with the peer (halo tagging), so the two ranks need a host thread each, as in the
