@@ -113,8 +113,6 @@ struct cb200_sim {
 	size_t phase_used = 0;
 	bool capturing = false;
 	bool owns_stream = false;
-	cudaStream_t side = nullptr;  // MGSP: halo g2p2g + send run here, concurrently with the interior g2p2g
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -575,9 +573,6 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 			CK(cudaMalloc(&s->interior_list[i], (mb + 1) * sizeof(int)));
 			s->interior_count[i] = s->mgsp_done + 8 + i;
 		}
-		CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	*out = s;
@@ -626,9 +621,6 @@ int cb200_sim_destroy(cb200_sim* s) {
 		cudaFree(s->interior_list[i]);
 	}
 	cudaFreeHost(s->h_state);
-	if(s->side) cudaStreamDestroy(s->side);
-	if(s->ev_fork) cudaEventDestroy(s->ev_fork);
-	if(s->ev_join) cudaEventDestroy(s->ev_join);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return 0;
@@ -866,14 +858,14 @@ int cb200_sim_advance_frame(cb200_sim* s, int* steps_taken) {
 		if(s->h_state->error) break;
 		const float left = frame - s->h_state->step_time;
 		if(!(left > 0.f)) break;
-		int batch = (int) ceilf(left / s->h_state->dt_default);
+		// dt never exceeds dt_default and the device clamps it to the time left, so floor(left / dt_default) sub-steps can
+		// be queued without looking at the device clock in between (one host sync per batch, none per sub-step)
+		int batch = (int) floorf(left / s->h_state->dt_default);
 		if(batch < 1) batch = 1;
-		if(batch > 64) batch = 64;
-		// never overshoot: the device clamps dt to the remaining time, and a zero-length step is harmless
-		int e = cb200_sim_step(s, 1);
+		if(batch > 4096) batch = 4096;
+		const int e = cb200_sim_step(s, batch);
 		if(e) return e;
-		taken += 1;
-		(void) batch;
+		taken += batch;
 	}
 	if(steps_taken) *steps_taken = taken;
 	return 0;

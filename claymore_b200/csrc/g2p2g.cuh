@@ -184,10 +184,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			sm.nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
 			sm.prevno[d] = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
 		}
-		{
-			float4* acc4 = reinterpret_cast<float4*>(sm.acc);
-			for(int i = tid; i < 8 * 256 / 4; i += T) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-		}
+		bool acc_dirty = true;  // the arena still feeds the previous block's bulk reductions: it is drained and zeroed just
+		                        // before this block's first accumulation, i.e. behind its whole phase 1
 		__syncthreads();
 		mbar_wait(bar, phase);
 		phase ^= 1;
@@ -424,7 +422,13 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				else if(it == 1) cr1 = cr;
 				else cr2 = cr;
 			}
+			if(acc_dirty && tid < 8) tma_wait_read<0>();  // the TMA unit has read the arena of the previous block
 			__syncthreads();
+			if(acc_dirty) {
+				float4* acc4 = reinterpret_cast<float4*>(sm.acc);
+				for(int i = tid; i < 8 * 256 / 4; i += T) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+				acc_dirty = false;
+			}
 			if(tid < 32) {
 				const int c0v = sm.cnt[2 * tid], c1v = sm.cnt[2 * tid + 1];
 				const int pair = c0v + c1v;
@@ -545,10 +549,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					}
 				}
 			}
-			tma_commit();
-			tma_wait_read<0>();
+			tma_commit();  // not waited for here: see acc_dirty
 		}
-		__syncthreads();
 	}
 	if(threadIdx.x < 8) tma_wait_all<0>();
 }

@@ -347,3 +347,24 @@ def test_reference_gpu_live_three_way(oracle, cuda_lib):
     compare_with_ref_gpu_golden(esim, golden, 10, 1, "engine vs live reference")
     ref.close()
     esim.close()
+
+
+def test_advance_frame_matches_reference_frame_loop(oracle, cuda_lib):
+    """main_loop's inner for-loop (gmpm_simulator.cuh:324): sub-steps until the frame time is reached, the last dt clamped."""
+    scene = scenes.small_cube()
+    fps, dt = 240, 1e-4
+    frame = np.float32(1.0 / fps)
+    osim = scenes.build_oracle(oracle, scene, dt=dt)
+    esim = scenes.build_engine(scene, dt=dt, fps=fps)
+    for f in range(2):
+        t, steps = np.float32(0.0), 0
+        while t < frame:
+            osim.step(1, time_left=float(frame - t))
+            t = np.float32(t + np.float32(osim.dt))
+            steps += 1
+        taken = esim.advance_frame()
+        assert taken == steps == 42, (taken, steps)
+        st = esim.stats()
+        assert st.error == 0 and abs(st.dt - osim.dt) <= 1e-9 and abs(st.step_time - float(frame)) <= 1e-7
+        _compare_state(osim, esim, 1, f"after frame {f + 1}", pos_tol=5e-6, f_tol=2e-4)
+    esim.close()
