@@ -124,6 +124,7 @@ _SIGNATURES = {
     "cb200_sim_sync": [_P],
     "cb200_sim_stats_get": [_P, C.POINTER(SimStats)],
     "cb200_sim_retrieve": [_P, _I, _P, C.POINTER(_I)],
+    "cb200_sim_retrieve_pinned": [_P, _I, C.POINTER(_P), C.POINTER(_I)],
     "cb200_sim_particle_state": [_P, _I, _P, C.POINTER(_I)],
     "cb200_sim_active_keys": [_P, _P, _I, C.POINTER(_I)],
     "cb200_sim_grid": [_P, _P, _I, C.POINTER(_I)],

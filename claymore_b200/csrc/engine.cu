@@ -43,6 +43,10 @@ struct Model {
 	int n = 0;
 	float v0[3] = {0, 0, 0};
 	int* bin_sizes = nullptr;
+	// output staging (retrieve): device buffer + pinned host mirror, grown on demand, reused across frames
+	float* d_out = nullptr;
+	float* h_out = nullptr;
+	size_t out_floats = 0;
 };
 
 void default_material(const cb200_config& cfg, int material, cb200_particle_buffer& pb) {
@@ -602,6 +606,8 @@ int cb200_sim_destroy(cb200_sim* s) {
 		}
 		cudaFree(m.d_pos);
 		cudaFree(m.bin_sizes);
+		cudaFree(m.d_out);
+		cudaFreeHost(m.h_out);
 	}
 	cudaFree(s->marks);
 	cudaFree(s->dest);
@@ -893,29 +899,43 @@ int cb200_sim_stats_get(cb200_sim* s, cb200_sim_stats* out) {
 	return 0;
 }
 
-static int retrieve_impl(cb200_sim* s, int model, float* host, int nch, int* n_out) {
+// output_model (gmpm_simulator.cuh:594-634): particles -> flat array -> host.  The staging buffers persist (the reference borrows
+// and re-allocates per frame) and the device->host copy lands in pinned memory; `host` == nullptr returns the pinned mirror itself.
+static int retrieve_impl(cb200_sim* s, int model, float* host, int nch, int* n_out, const float** pinned_out) {
 	if(!s || !s->setup_done || model < 0 || model >= (int) s->models.size()) return (int) cudaErrorInvalidValue;
 	Model& m = s->models[model];
 	const int R = s->rollid, Rn = R ^ 1;
-	float* d_out = nullptr;
-	CK(cudaMalloc(&d_out, (size_t) m.n * nch * sizeof(float)));
+	const size_t need = (size_t) m.n * nch;
+	if(m.out_floats < need) {
+		cudaFree(m.d_out);
+		cudaFreeHost(m.h_out);
+		m.d_out = nullptr;
+		m.h_out = nullptr;
+		CK(cudaMalloc(&m.d_out, need * sizeof(float)));
+		m.out_floats = need;
+	}
+	if(!host && !m.h_out) CK(cudaMallocHost(&m.h_out, m.out_floats * sizeof(float)));
+	float* dst = host ? host : m.h_out;  // caller memory (fast when it is pinned) or the simulator's pinned mirror
 	CK(cudaMemsetAsync(s->d_scratch + 2, 0, sizeof(int), s->stream));
-	retrieve_kernel<<<num_sms() * 8, 128, 0, s->stream>>>(s->cfg, m.material, count_dev(&s->d_state->pbc), s->part[R].active_keys, s->part[Rn].index_table, view(m.pb[R]), view(m.pb[Rn]), d_out, nch, s->d_scratch + 2);
+	retrieve_kernel<<<num_sms() * 8, 128, 0, s->stream>>>(s->cfg, m.material, count_dev(&s->d_state->pbc), s->part[R].active_keys, s->part[Rn].index_table, view(m.pb[R]), view(m.pb[Rn]), m.d_out, nch, s->d_scratch + 2);
 	++s->launches;
+	// the count is only known on the device: copy the full staging buffer behind the kernel, read the count with it
+	CK(cudaMemcpyAsync(dst, m.d_out, need * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	int n = 0;
 	CK(cudaMemcpyAsync(&n, s->d_scratch + 2, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	if(n > m.n) n = m.n;
-	CK(cudaMemcpy(host, d_out, (size_t) n * nch * sizeof(float), cudaMemcpyDeviceToHost));
-	cudaFree(d_out);
+	if(pinned_out) *pinned_out = m.h_out;
 	if(n_out) *n_out = n;
 	return 0;
 }
-int cb200_sim_retrieve(cb200_sim* s, int model, float* positions_host, int* n_out) { return retrieve_impl(s, model, positions_host, 3, n_out); }
+int cb200_sim_retrieve(cb200_sim* s, int model, float* positions_host, int* n_out) { return retrieve_impl(s, model, positions_host, 3, n_out, nullptr); }
+// zero-copy variant: *positions_pinned points at the simulator's pinned staging buffer (valid until the next retrieve of that model)
+int cb200_sim_retrieve_pinned(cb200_sim* s, int model, const float** positions_pinned, int* n_out) { return retrieve_impl(s, model, nullptr, 3, n_out, positions_pinned); }
 int cb200_sim_particle_state(cb200_sim* s, int model, float* state_host, int* n_out) {
 	if(!s || model < 0 || model >= (int) s->models.size()) return (int) cudaErrorInvalidValue;
 	const int mat = s->models[model].material;
-	return retrieve_impl(s, model, state_host, mat == CB200_J_FLUID ? 4 : (mat == CB200_FIXED_COROTATED ? 12 : 13), n_out);
+	return retrieve_impl(s, model, state_host, mat == CB200_J_FLUID ? 4 : (mat == CB200_FIXED_COROTATED ? 12 : 13), n_out, nullptr);
 }
 
 int cb200_sim_active_keys(cb200_sim* s, int* keys_host, int capacity_blocks, int* n_out) {

@@ -114,6 +114,7 @@ def bench_mgsp(args, scene, label, rank, world, local_rank):
     # end to end: upload from pinned host memory, setup, K x (step + D2H stats), download -- on every rank, max over ranks
     sim.close()
     pinned = [torch.from_numpy(m["pos"]).pin_memory() for m in part["models"]]
+    out_pinned = [torch.empty_like(p).pin_memory() for p in pinned]
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -124,7 +125,7 @@ def bench_mgsp(args, scene, label, rank, world, local_rank):
     for _ in range(args.steps):
         sim2.step(1)
         s2 = sim2.stats()
-    got = sum(len(sim2.retrieve(i)) for i in range(len(part["models"])))
+    got = sum(len(sim2.retrieve(i, out=out_pinned[i].numpy())) for i in range(len(part["models"])))
     torch.cuda.synchronize()
     t = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

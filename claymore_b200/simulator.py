@@ -106,11 +106,18 @@ class GmpmSimulator:
         st = self.stats()
         return st.particle_block_count, st.neighbor_block_count, st.exterior_block_count
 
-    def retrieve(self, model):
-        out = np.zeros((self.counts[model], 3), np.float32)
-        n = C.c_int(0)
-        check(self.L.cb200_sim_retrieve(self.h, model, out.ctypes.data_as(C.c_void_p), C.byref(n)), "retrieve")
-        return out[: n.value]
+    def retrieve(self, model, copy=True, out=None):
+        """Positions of one model (output_model).  out: caller-owned float32 array of shape (count, 3) (pinned memory makes
+        the device->host copy fast); otherwise copy=False returns a view of the simulator's pinned staging buffer, valid until
+        the next retrieve of that model."""
+        n, p = C.c_int(0), C.c_void_p()
+        if out is not None:
+            assert out.dtype == np.float32 and out.size >= 3 * self.counts[model] and out.flags.c_contiguous
+            check(self.L.cb200_sim_retrieve(self.h, model, out.ctypes.data_as(C.c_void_p), C.byref(n)), "retrieve")
+            return out.reshape(-1, 3)[: n.value]
+        check(self.L.cb200_sim_retrieve_pinned(self.h, model, C.byref(p), C.byref(n)), "retrieve")
+        view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value, 3))
+        return view.copy() if copy else view
 
     def particle_state(self, model):
         nch = CHANNELS[self.materials[model]]

@@ -180,6 +180,8 @@ CB200_API int cb200_sim_sync(cb200_sim* sim);
 CB200_API int cb200_sim_stats_get(cb200_sim* sim, cb200_sim_stats* out); /* synchronises */
 /* output_model  gmpm_simulator.cuh:594-634: positions to HOST float[3*n]; returns count in *n_out */
 CB200_API int cb200_sim_retrieve(cb200_sim* sim, int model, float* positions_host, int* n_out);
+/* same, zero-copy: *positions_pinned is the simulator's pinned staging buffer, valid until the next retrieve of that model */
+CB200_API int cb200_sim_retrieve_pinned(cb200_sim* sim, int model, const float** positions_pinned, int* n_out);
 /* full particle state (all channels, [n][channels]) to HOST, same traversal as retrieve */
 CB200_API int cb200_sim_particle_state(cb200_sim* sim, int model, float* state_host, int* n_out);
 /* copies for parity checks: active keys (int[3*ebc]) and grid blocks of grid[0] (float[256*nbc]) to HOST */
