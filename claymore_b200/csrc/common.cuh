@@ -125,6 +125,34 @@ __device__ __forceinline__ int table_query(const Cfg& c, const int* __restrict__
 // get_block_id (utility_funcs.hpp:21-23): round-half-away-from-zero of p * dx_inv
 __device__ __forceinline__ int cell_index(const Cfg& c, float p) { return __float2int_rn(roundf(p * c.dx_inv)); }
 
+// compute_dt (utility_funcs.hpp:36-49) evaluated on the device from the reduced max |v|^2
+__device__ __forceinline__ float device_compute_dt(const Cfg& cfg, float max_vel_sq, float step_time, float frame_time, float dt_default) {
+	float dt = dt_default;
+	const float mv = sqrtf(max_vel_sq);
+	if(mv > 0.f) dt = fminf(dt, cfg.dx * cfg.cfl / mv);
+	if(frame_time > 0.f) dt = fminf(dt, frame_time - step_time);
+	return dt;
+}
+
+// max |v|^2 of the two cells a lane holds of a grid block, computed exactly as the grid update will compute it
+// (update_grid_velocity_query_max, mgmpm_kernels.cuh:339-388): wall mask, then gravity on y, NaN -> +inf
+__device__ __forceinline__ float cell_pair_vel_sq(float2 m, float2 v0, float2 v1, float2 v2, bool wx, bool wy, bool wz, float gdt) {
+	float sq0 = 0.f, sq1 = 0.f;
+	if(m.x > 0.f) {
+		const float mi = 1.f / m.x;
+		const float a = wx ? 0.f : v0.x * mi, b = (wy ? 0.f : v1.x * mi) + gdt, c = wz ? 0.f : v2.x * mi;
+		sq0 = a * a + b * b + c * c;
+	}
+	if(m.y > 0.f) {
+		const float mi = 1.f / m.y;
+		const float a = wx ? 0.f : v0.y * mi, b = (wy ? 0.f : v1.y * mi) + gdt, c = wz ? 0.f : v2.y * mi;
+		sq1 = a * a + b * b + c * c;
+	}
+	if(isnan(sq0)) sq0 = INFINITY;
+	if(isnan(sq1)) sq1 = INFINITY;
+	return fmaxf(sq0, sq1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // sm_100a async-proxy primitives (TMA 1-D bulk copy / bulk reduce, mbarrier)
 // ------------------------------------------------------------------------------------------------

@@ -206,6 +206,12 @@ int enqueue_grid_update(cb200_sim* s, int R) {
 	gu.keys = s->part[R].active_keys;
 	gu.max_vel = &s->d_state->max_vel_sq;
 	gu.clear_grid = s->grid[1];
+	if(s->desc.mgsp_world > 1) {
+		// the global max |v|^2 was agreed on at the end of the previous sub-step (it rides on the key exchange) and the next grid
+		// was cleared there as well, before the peers were told they may reduce into it
+		gu.max_vel = reinterpret_cast<float*>(s->d_scratch + 5);
+		gu.clear_grid = nullptr;
+	}
 	gu.n_clear = (int) s->models.size();
 	for(size_t m = 0; m < s->models.size(); ++m) gu.clear_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
 	grid_update_kernel<<<grid_blocks(4), kGridThreads, 0, s->stream>>>(gu);
@@ -327,11 +333,28 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 	}
 	return (int) cudaGetLastError();
 }
+int mark_phase(cb200_sim* s, int id);
+int enqueue_halo_publish(cb200_sim* s, int P, const float* local_max);
+int enqueue_halo_tag_reset(cb200_sim* s, int P);
+int enqueue_halo_tag(cb200_sim* s, int P, const int* particle_block_count, const float* local_max, float* global_max);
+
+// End of a sub-step.  Single GPU: snapshot the neighbour count, carry the grid, register exterior blocks, roll the state.
+// MGSP: the same, interleaved with the end-of-step exchange so that its wait sits behind local work:
+//   snapshot, reset tags -> carry (+ this rank's max |v|^2 of the new grid) -> clear the next grid -> PUBLISH keys + max
+//   -> register exterior blocks -> WAIT for the peers' messages, tag overlaps, global max -> halo block lists -> roll the state.
+// A peer may reduce into this rank's next grid as soon as it has seen this rank's message: the clear comes before the publish.
 int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 	const int Rn = R ^ 1;
 	cudaStream_t st = s->stream;
+	const bool mgsp = s->desc.mgsp_world > 1;
+	float* local_max = reinterpret_cast<float*>(s->d_scratch + 3);
+	float* global_max = reinterpret_cast<float*>(s->d_scratch + 4);
 	snapshot_int_kernel<<<1, 32, 0, st>>>(s->part[Rn].count, s->d_scratch + 1);
 	++s->launches;
+	if(mgsp) {
+		CK(cudaMemsetAsync(local_max, 0, sizeof(float), st));
+		CK(enqueue_halo_tag_reset(s, Rn));
+	}
 	{
 		CarryArgs a {};
 		a.cfg = s->cfg;
@@ -341,8 +364,14 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		a.state = s->d_state;
 		a.old_grid = s->grid[1];
 		a.new_grid = s->grid[0];
+		a.next_max_vel = mgsp ? local_max : nullptr;
 		carry_grid_kernel<<<grid_blocks(4), 256, 0, st>>>(a);
 		++s->launches;
+	}
+	if(mgsp) {
+		clear_grid_dev_kernel<<<grid_blocks(4), 256, 0, st>>>(s->d_scratch + 1, s->grid[1]);
+		++s->launches;
+		CK(enqueue_halo_publish(s, Rn, local_max));
 	}
 	{
 		RegisterArgs a {};
@@ -358,6 +387,11 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		register_blocks_kernel<<<grid_blocks(4), 128, 0, st>>>(a);
 		++s->launches;
 	}
+	if(mgsp) {
+		mark_phase(s, 9);
+		CK(enqueue_halo_tag(s, Rn, s->d_scratch + 0, local_max, global_max));
+		mark_phase(s, 8);
+	}
 	{
 		FinalizeArgs a {};
 		a.cfg = s->cfg;
@@ -368,6 +402,7 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		a.max_blocks = s->desc.max_blocks;
 		a.n_models = (int) s->models.size();
 		for(size_t m = 0; m < s->models.size(); ++m) a.bin_capacity[m] = s->models[m].bin_capacity;
+		a.next_max_vel = mgsp ? global_max : nullptr;
 		finalize_step_kernel<<<1, 32, 0, st>>>(a);
 		++s->launches;
 	}
@@ -400,14 +435,25 @@ int enqueue_halo_reduce(cb200_sim* s, int g, int P) {
 	return (int) cudaGetLastError();
 }
 // halo_tagging (mgsp_benchmark.cuh:661-720) on partition P whose Partition::count currently equals its neighbour count
-int enqueue_halo_tagging(cb200_sim* s, int P, const int* particle_block_count) {
+// key_limit: device int holding the neighbour count of partition P (its Partition::count may already include exterior blocks)
+int enqueue_halo_publish(cb200_sim* s, int P, const float* local_max) {
 	cudaStream_t st = s->stream;
 	const MgspView v = mgsp_view(s);
-	mgsp_tag_reset_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].overlap_marks, s->part[P].count, s->part[P].halo_count, s->interior_count[P]);
-	mgsp_publish_keys_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].active_keys, s->part[P].count);
-	mgsp_tag_kernel<<<grid_blocks(1), 256, 0, st>>>(s->cfg, v, s->part[P].index_table, s->part[P].overlap_marks);
+	mgsp_publish_keys_kernel<<<grid_blocks(1), 256, 0, st>>>(v, s->part[P].active_keys, s->d_scratch + 1, local_max);
+	++s->launches;
+	return (int) cudaGetLastError();
+}
+int enqueue_halo_tag_reset(cb200_sim* s, int P) {
+	mgsp_tag_reset_kernel<<<grid_blocks(1), 256, 0, s->stream>>>(mgsp_view(s), s->part[P].overlap_marks, s->d_scratch + 1, s->part[P].halo_count, s->interior_count[P]);
+	++s->launches;
+	return (int) cudaGetLastError();
+}
+int enqueue_halo_tag(cb200_sim* s, int P, const int* particle_block_count, const float* local_max, float* global_max) {
+	cudaStream_t st = s->stream;
+	const MgspView v = mgsp_view(s);
+	mgsp_tag_kernel<<<grid_blocks(1), 256, 0, st>>>(s->cfg, v, s->part[P].index_table, s->part[P].overlap_marks, s->d_scratch + 1, local_max, global_max);
 	collect_halo_blockids_kernel<<<grid_blocks(2), 128, 0, st>>>(s->cfg, count_dev(particle_block_count), s->part[P].index_table, s->part[P].active_keys, s->part[P].overlap_marks, s->part[P].halo_marks, s->part[P].halo_count, nullptr, s->halo_list[P], s->interior_list[P], s->interior_count[P]);
-	s->launches += 4;
+	s->launches += 2;
 	return (int) cudaGetLastError();
 }
 
@@ -432,10 +478,6 @@ int enqueue_substep(cb200_sim* s, int R) {
 	if((e = enqueue_grid_update(s, R))) return e;
 	mark_phase(s, 1);
 	if(s->desc.mgsp_world > 1) {
-		// dt must be the same on every rank: all-reduce(max) of |v|^2 (host max over devices in the reference, :410-416)
-		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s), &s->d_state->max_vel_sq);
-		++s->launches;
-		mark_phase(s, 2);
 		// ONE g2p2g launch: the arena flush of a block reduces into this rank's next grid and, for grid blocks shared with a
 		// peer, straight into that peer's next grid over NVLink (no pack, no send, no unpack kernels; the reference: halo g2p2g,
 		// barrier, collect_grid_blocks + cudaMemcpyPeerAsync, non-halo g2p2g, barrier, reduce_grid_blocks; :421-467, 723-776).
@@ -448,9 +490,7 @@ int enqueue_substep(cb200_sim* s, int R) {
 		mark_phase(s, 6);
 		if((e = enqueue_rebuild(s, R))) return e;
 		mark_phase(s, 7);
-		if((e = enqueue_halo_tagging(s, R ^ 1, s->d_scratch + 0))) return e;  // (:530)
-		mark_phase(s, 8);
-		if((e = enqueue_carry_and_exterior(s, R))) return e;
+		if((e = enqueue_carry_and_exterior(s, R))) return e;  // includes the key / max-velocity exchange and the halo tagging (:530)
 		mark_phase(s, 9);
 		return 0;
 	}
@@ -505,6 +545,8 @@ void preload_kernels() {
 	preload(mgsp_tag_reset_kernel);
 	preload(mgsp_tag_kernel);
 	preload(mgsp_done_barrier_kernel);
+	preload(clear_grid_dev_kernel);
+	preload(grid_max_kernel);
 	g2p2g_prepare_all();
 }
 int ensure_graph(cb200_sim* s, int R) {
@@ -755,7 +797,11 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 		if(s->desc.mgsp_world > 1) {  // halo_tagging of the initial partition (mgsp_benchmark.cuh:633)
 			if(!s->peers_ready) return (int) cudaErrorNotReady;
 			CK(cudaMemcpyAsync(s->d_scratch + 0, &pbc, sizeof(int), cudaMemcpyHostToDevice, st));
-			CK(enqueue_halo_tagging(s, Rn, s->d_scratch + 0));
+			CK(cudaMemcpyAsync(s->d_scratch + 1, &nbc, sizeof(int), cudaMemcpyHostToDevice, st));
+			CK(cudaMemsetAsync(s->d_scratch + 3, 0, 2 * sizeof(int), st));
+			CK(enqueue_halo_tag_reset(s, Rn));
+			CK(enqueue_halo_publish(s, Rn, reinterpret_cast<float*>(s->d_scratch + 3)));
+			CK(enqueue_halo_tag(s, Rn, s->d_scratch + 0, reinterpret_cast<float*>(s->d_scratch + 3), reinterpret_cast<float*>(s->d_scratch + 4)));
 		}
 		a.lo = -1;
 		a.span = 3;
@@ -822,6 +868,12 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	h.next_dt = dt;
 	h.max_vel_sq = 0.f;
 	CK(push_state(s));
+	if(s->desc.mgsp_world > 1) {
+		// global max |v|^2 of the start grid (later sub-steps get it from the end-of-step exchange of the previous one)
+		grid_max_kernel<<<grid_blocks(2), 256, 0, st>>>(cfg, s->d_state, s->grid[0], s->part[R].active_keys, &s->d_state->max_vel_sq);
+		mgsp_allreduce_maxvel_kernel<<<1, 32, 0, st>>>(mgsp_view(s), &s->d_state->max_vel_sq);
+		s->launches += 2;
+	}
 	CK(cudaStreamSynchronize(st));
 	if(s->desc.use_graph) {  // instantiate both roll parities now: never later, while a peer may be waiting on this rank
 		CK(ensure_graph(s, 0));

@@ -72,15 +72,6 @@ struct G2P2GArgs {
 	float* peer_grid[8];
 };
 
-// compute_dt (utility_funcs.hpp:36-49) evaluated on the device from the reduced max |v|^2
-__device__ __forceinline__ float device_compute_dt(const Cfg& cfg, float max_vel_sq, float step_time, float frame_time, float dt_default) {
-	float dt = dt_default;
-	const float mv = sqrtf(max_vel_sq);
-	if(mv > 0.f) dt = fminf(dt, cfg.dx * cfg.cfl / mv);
-	if(frame_time > 0.f) dt = fminf(dt, frame_time - step_time);
-	return dt;
-}
-
 // accumulation arena: [block 2x2x2][channel 4][cell 4x4x4] floats == eight grid blocks back to back
 __device__ __forceinline__ int acc_off_x(int X) { return ((X >> 2) << 2) * 256 + ((X & 3) << 4); }
 __device__ __forceinline__ int acc_off_y(int Y) { return ((Y >> 2) << 1) * 256 + ((Y & 3) << 2); }

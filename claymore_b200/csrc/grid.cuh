@@ -92,6 +92,13 @@ __global__ void clear_grid_kernel(int block_count, float* grid) {
 	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// clear_grid with a device-resident block count
+__global__ void clear_grid_dev_kernel(const int* block_count, float* grid) {
+	const size_t n4 = (size_t) *block_count * (kGridBlockFloats / 4);
+	float4* g = reinterpret_cast<float4*>(grid);
+	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Carry of the next-grid into the new numbering.  The reference clears grid[0] and scatters marked blocks
 // through the new table (clear_grid + copy_selected_grid_blocks, mgmpm_kernels.cuh:1002-1020,
 // gmpm_simulator.cuh:536-541).  Here every block of the NEW numbering pulls its source through the OLD table:
@@ -105,23 +112,55 @@ struct CarryArgs {
 	const StepState* state; // old nbc = state->nbc
 	const float* old_grid;
 	float* new_grid;
+	float* next_max_vel;    // nullable (MGSP): max |v|^2 the NEXT grid update will find on this rank, so that the all-reduce
+	                        // of it can ride on the end-of-step key exchange instead of being a sync point of its own
 };
 __global__ void __launch_bounds__(256) carry_grid_kernel(const CarryArgs a) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = *a.new_count;
 	const int old_nbc = a.state->nbc;
+	const int g = a.cfg.gsize, bc = a.cfg.boundary;
+	float gdt = 0.f;
+	if(a.next_max_vel) gdt = a.cfg.gravity * device_compute_dt(a.cfg, a.state->max_vel_sq, a.state->step_time, a.state->frame_time, a.state->dt_default);
+	unsigned vmax = 0u;
 	for(int j = blockIdx.x * 8 + warp; j < n; j += gridDim.x * 8) {
-		const int src = table_query(a.cfg, a.old_table, a.new_keys[3 * j], a.new_keys[3 * j + 1], a.new_keys[3 * j + 2]);
+		const int kx = a.new_keys[3 * j], ky = a.new_keys[3 * j + 1], kz = a.new_keys[3 * j + 2];
+		const int src = table_query(a.cfg, a.old_table, kx, ky, kz);
 		float4* d = reinterpret_cast<float4*>(a.new_grid + (size_t) j * kGridBlockFloats);
 		if(src >= 0 && src < old_nbc) {
 			const float4* s = reinterpret_cast<const float4*>(a.old_grid + (size_t) src * kGridBlockFloats);
 			d[lane] = s[lane];
 			d[32 + lane] = s[32 + lane];
+			if(a.next_max_vel) {
+				const float2* s2 = reinterpret_cast<const float2*>(s);
+				const bool wx = (kx < bc) | (kx >= g - bc), wy = (ky < bc) | (ky >= g - bc), wz = (kz < bc) | (kz >= g - bc);
+				vmax = max(vmax, __float_as_uint(cell_pair_vel_sq(s2[lane], s2[32 + lane], s2[64 + lane], s2[96 + lane], wx, wy, wz, gdt)));
+			}
 		} else {
 			d[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
 			d[32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
 		}
 	}
+	if(a.next_max_vel) {
+		vmax = __reduce_max_sync(0xffffffffu, vmax);
+		if(lane == 0 && vmax) atomicMax(reinterpret_cast<unsigned*>(a.next_max_vel), vmax);
+	}
+}
+
+// max |v|^2 the grid update will find, without touching the grid (MGSP start-up)
+__global__ void __launch_bounds__(256) grid_max_kernel(Cfg cfg, const StepState* state, const float* grid, const int* keys, float* max_vel) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = cfg.gsize, bc = cfg.boundary;
+	const float gdt = cfg.gravity * state->dt;
+	unsigned vmax = 0u;
+	for(int b = blockIdx.x * 8 + warp; b < state->nbc; b += gridDim.x * 8) {
+		const int kx = keys[3 * b], ky = keys[3 * b + 1], kz = keys[3 * b + 2];
+		const bool wx = (kx < bc) | (kx >= g - bc), wy = (ky < bc) | (ky >= g - bc), wz = (kz < bc) | (kz >= g - bc);
+		const float2* s2 = reinterpret_cast<const float2*>(grid + (size_t) b * kGridBlockFloats);
+		vmax = max(vmax, __float_as_uint(cell_pair_vel_sq(s2[lane], s2[32 + lane], s2[64 + lane], s2[96 + lane], wx, wy, wz, gdt)));
+	}
+	vmax = __reduce_max_sync(0xffffffffu, vmax);
+	if(lane == 0 && vmax) atomicMax(reinterpret_cast<unsigned*>(max_vel), vmax);
 }
 
 // copy_selected_grid_blocks (mgmpm_kernels.cuh:1002-1020), drop-in form: scatter marked blocks

@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(256) mgsp_wait_reduce_kernel(Cfg cfg, MgspView
 }
 
 // ---- key all-gather for halo tagging (halo_tagging, mgsp_benchmark.cuh:661-720) -----------------------------------
-__global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, const int* keys, const int* key_count) {
+// The message also carries this rank's max |v|^2 of the grid the NEXT sub-step starts from (computed by the carry kernel), so
+// that the tag kernel, which waits for every peer's message anyway, yields the global maximum: one sync point per sub-step less.
+__global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, const int* keys, const int* key_count, const float* local_max_vel) {
 	const int epoch = v.epochs[2] + 1, par = epoch & 1;
 	const int n3 = min(*key_count, v.L.max_blocks) * 3;
 	for(int p = 0; p < v.world; ++p) {
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, cons
 		if((int) threadIdx.x < v.world && (int) threadIdx.x != v.rank) {
 			InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, threadIdx.x, par, v.rank));
 			h->key_count = n3 / 3;
+			h->max_vel_sq = *local_max_vel;
 			__threadfence_system();
 			st_release_sys(&h->flag_keys, epoch);
 		}
@@ -249,7 +252,10 @@ __global__ void mgsp_tag_reset_kernel(MgspView v, int* overlap_marks, const int*
 }
 
 // mark_overlapping_blocks for every peer (halo_kernels.cuh:22-35), keys read from my inbox
-__global__ void __launch_bounds__(256) mgsp_tag_kernel(Cfg cfg, MgspView v, const int* table, int* overlap_marks) {
+// key_limit: only blocks numbered below it (particle + neighbour blocks) can overlap; exterior blocks registered meanwhile are ignored
+__global__ void __launch_bounds__(256) mgsp_tag_kernel(Cfg cfg, MgspView v, const int* table, int* overlap_marks, const int* key_limit, const float* local_max_vel, float* global_max_vel) {
+	const int limit = *key_limit;
+	float gmax = *local_max_vel;
 	const int epoch = v.epochs[2] + 1, par = epoch & 1;
 	for(int p = 0; p < v.world; ++p) {
 		if(p == v.rank) continue;
@@ -258,12 +264,13 @@ __global__ void __launch_bounds__(256) mgsp_tag_kernel(Cfg cfg, MgspView v, cons
 		if(threadIdx.x == 0) wait_flag(&hd->flag_keys, epoch);
 		__syncthreads();
 		const int n = *reinterpret_cast<volatile int*>(&hd->key_count);
+		gmax = fmaxf(gmax, *reinterpret_cast<volatile float*>(&hd->max_vel_sq));
 		const int* rk = reinterpret_cast<const int*>(seg + v.L.off_keys);
 		int* outk = v.overlap_keys + (size_t) p * v.L.max_blocks * 3;
 		for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 			const int x = rk[3 * i], y = rk[3 * i + 1], z = rk[3 * i + 2];
 			const int bno = table_query(cfg, table, x, y, z);
-			if(bno >= 0) {
+			if(bno >= 0 && bno < limit) {
 				atomicOr(overlap_marks + bno, 1 << p);
 				v.peer_bno[(size_t) p * v.L.max_blocks + bno] = i;  // the peer's keys arrive in its block order
 				const int h = atomicAdd(&v.overlap_count[p], 1);
@@ -282,6 +289,7 @@ __global__ void __launch_bounds__(256) mgsp_tag_kernel(Cfg cfg, MgspView v, cons
 	if(s_last && threadIdx.x == 0) {
 		v.done[3] = 0;
 		v.epochs[2] = epoch;
+		*global_max_vel = gmax;  // every CTA saw every header; the last one publishes
 	}
 }
 

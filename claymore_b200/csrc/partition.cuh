@@ -307,6 +307,7 @@ struct FinalizeArgs {
 	int max_blocks;
 	int n_models;
 	long long bin_capacity[kMaxModels];
+	const float* next_max_vel;  // nullable (MGSP): global max |v|^2 of the grid the next sub-step starts from
 };
 __global__ void finalize_step_kernel(const FinalizeArgs a) {
 	if(threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -328,7 +329,7 @@ __global__ void finalize_step_kernel(const FinalizeArgs a) {
 		if(s->bin_count[m] > a.bin_capacity[m]) s->error |= kErrBinCapacity;
 	s->dt = next_dt;
 	s->step_time += next_dt;
-	s->max_vel_sq = 0.f;
+	s->max_vel_sq = a.next_max_vel ? *a.next_max_vel : 0.f;
 	s->work_counter = 0;
 	s->work_counter2 = 0;
 	s->steps += 1;

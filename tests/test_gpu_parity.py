@@ -227,15 +227,17 @@ def test_grid_update_kernel_differential(oracle, cuda_lib):
 
 # ---- MGSP: two particle shards, exchange through peer inboxes (both ranks on ONE GPU, one host thread each) -----------
 @pytest.mark.timeout(300)
-def test_mgsp_two_shards_match_single_domain(oracle, cuda_lib):
+@pytest.mark.parametrize("v0,dt_default", [((0.3, -1.0, 0.2), 1e-4), ((1.0, -10.0, 0.5), 1e-3)], ids=["dt_default_binds", "cfl_binds"])
+def test_mgsp_two_shards_match_single_domain(oracle, cuda_lib, v0, dt_default):
+    """cfl_binds: dt follows the max grid velocity, so the ranks must agree on the all-reduced maximum bit for bit."""
     import threading
     from claymore_b200 import mgsp
-    scene = scenes.small_cube()
-    osim = scenes.build_oracle(oracle, scene)
+    scene = scenes.small_cube(v0=v0)
+    osim = scenes.build_oracle(oracle, scene, dt=dt_default)
     sims = []
     for r in range(2):
         part = mgsp.partition_scene(scene, r, 2)
-        sims.append(mgsp.build_rank_sim(part, r, 2, 1e-4, 4000, scenes.apply_material))
+        sims.append(mgsp.build_rank_sim(part, r, 2, dt_default, 4000, scenes.apply_material))
     ptrs = [s.mgsp_inbox() for s in sims]
     for s in sims:
         s.mgsp_set_peers(ptrs)
@@ -290,6 +292,9 @@ def test_mgsp_two_shards_match_single_domain(oracle, cuda_lib):
         idx = scenes.match_particles(so, se, tol=3e-6)
         assert np.abs(se[idx][:, 3:] - so[:, 3:]).max() <= 1e-4, label
         assert abs(sims[0].stats().dt - sims[1].stats().dt) == 0.0
+        assert abs(sims[0].stats().dt - osim.dt) <= 1e-6 * osim.dt
+        if dt_default > 5e-4:
+            assert osim.dt < dt_default  # the CFL bound is the one that binds in this variant
 
     check("after setup")
     for k in range(3):
