@@ -178,7 +178,8 @@ def run_reference(args):
 
 
 def run_b200(args):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 prints exactly one JSON line on stdout: NCCL's banner / debug lines (the box exports NCCL_DEBUG) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import scenes
