@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -87,6 +87,14 @@ class ClockSampler:
                 self.rows.append(line.strip())
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 3.0:   # the first sample takes a few hundred ms: wait for it
+            time.sleep(0.01)
+        self.first = len(self.rows)
+
+    def mark(self):
+        """Samples from here on are 'under load' (warm-up, timed region, per-kernel timing pass)."""
+        self.first = len(self.rows)
 
     def stop(self):
         if not self.proc:
@@ -97,7 +105,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[max(getattr(self, "first", 0) - 1, 0):]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -215,12 +223,13 @@ def run_b200(args):
 
     # ---- device-resident timing: K sub-steps, CUDA events, graph replay --------------------------------------
     sim = fresh(use_graph=not args.no_graph)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    clocks.mark()
     sim.step(args.warmup)
     sim.sync()
     st0 = sim.stats()
     assert st0.error == 0, f"engine error bits {st0.error} after warm-up"
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     l0 = sim.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

@@ -133,6 +133,7 @@ _SIGNATURES = {
     "cb200_sim_mgsp_open_peers": [_P, _P],
     "cb200_sim_mgsp_set_peers": [_P, C.POINTER(_P), C.POINTER(_P)],
     "cb200_sim_mgsp_halo_counts": [_P, C.POINTER(_I), C.POINTER(_I)],
+    "cb200_trim_pool": [],
     "cb200_sim_profile": [_P, _I],
     "cb200_sim_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(_I)],
     "cb200_sim_profile_phases": [_P, C.POINTER(C.c_double)],

@@ -13,6 +13,8 @@
 // the Python host layer (claymore_b200/scene.py).
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "g2p2g.cuh"
@@ -35,6 +37,63 @@ using namespace cb200;
 	} while(0)
 
 namespace {
+// Device-memory pool.  The reference frees and re-allocates its containers through raw cudaMalloc/cudaFree
+// (GmpmSimulator::DeviceAllocator, gmpm_simulator.cuh:40-51); multi-GB cudaFree/cudaMalloc pairs cost tens to hundreds
+// of milliseconds, so released blocks are kept (per device, exact size) and handed out again.  cb200_trim_pool() returns
+// everything to the driver.  Buffers exposed through CUDA IPC are never pooled.
+class DevicePool {
+public:
+	cudaError_t alloc(void** p, size_t bytes) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			auto it = free_.find({dev, bytes});
+			if(it != free_.end()) {
+				*p = it->second;
+				free_.erase(it);
+				live_[*p] = {dev, bytes};
+				return cudaSuccess;
+			}
+		}
+		cudaError_t e = cudaMalloc(p, bytes);
+		if(e == cudaErrorMemoryAllocation) {
+			cudaGetLastError();
+			trim();
+			e = cudaMalloc(p, bytes);
+		}
+		if(e == cudaSuccess) {
+			std::lock_guard<std::mutex> g(mu_);
+			live_[*p] = {dev, bytes};
+		}
+		return e;
+	}
+	void release(void* p) {
+		if(!p) return;
+		std::lock_guard<std::mutex> g(mu_);
+		auto it = live_.find(p);
+		if(it == live_.end()) {
+			cudaFree(p);
+			return;
+		}
+		free_.emplace(it->second, p);
+		live_.erase(it);
+	}
+	void trim() {
+		std::lock_guard<std::mutex> g(mu_);
+		for(auto& kv : free_) cudaFree(kv.second);
+		free_.clear();
+	}
+
+private:
+	std::mutex mu_;
+	std::map<void*, std::pair<int, size_t>> live_;
+	std::multimap<std::pair<int, size_t>, void*> free_;
+};
+DevicePool g_pool;
+template<typename T>
+cudaError_t pool_alloc(T** p, size_t bytes) { return g_pool.alloc(reinterpret_cast<void**>(p), bytes); }
+
 struct Model {
 	int material = 0;
 	cb200_particle_buffer pb[2];
@@ -122,12 +181,12 @@ struct cb200_sim {
 namespace {
 int alloc_partition(cb200_sim* s, cb200_partition& p) {
 	const size_t mb = (size_t) s->desc.max_blocks;
-	CK(cudaMalloc(&p.count, sizeof(int)));
-	CK(cudaMalloc(&p.index_table, s->table_entries * sizeof(int)));
-	CK(cudaMalloc(&p.active_keys, (mb + 1) * 3 * sizeof(int)));
-	CK(cudaMalloc(&p.halo_count, sizeof(int)));
-	CK(cudaMalloc(&p.halo_marks, mb + 1));
-	CK(cudaMalloc(&p.overlap_marks, (mb + 1) * sizeof(int)));
+	CK(pool_alloc(&p.count, sizeof(int)));
+	CK(pool_alloc(&p.index_table, s->table_entries * sizeof(int)));
+	CK(pool_alloc(&p.active_keys, (mb + 1) * 3 * sizeof(int)));
+	CK(pool_alloc(&p.halo_count, sizeof(int)));
+	CK(pool_alloc(&p.halo_marks, mb + 1));
+	CK(pool_alloc(&p.overlap_marks, (mb + 1) * sizeof(int)));
 	p.halo_blocks = nullptr;
 	CK(cudaMemsetAsync(p.count, 0, sizeof(int), s->stream));
 	CK(cudaMemsetAsync(p.index_table, 0xff, s->table_entries * sizeof(int), s->stream));
@@ -138,12 +197,12 @@ int alloc_partition(cb200_sim* s, cb200_partition& p) {
 	return 0;
 }
 void free_partition(cb200_partition& p) {
-	cudaFree(p.count);
-	cudaFree(p.index_table);
-	cudaFree(p.active_keys);
-	cudaFree(p.halo_count);
-	cudaFree(p.halo_marks);
-	cudaFree(p.overlap_marks);
+	g_pool.release(p.count);
+	g_pool.release(p.index_table);
+	g_pool.release(p.active_keys);
+	g_pool.release(p.halo_count);
+	g_pool.release(p.halo_marks);
+	g_pool.release(p.overlap_marks);
 }
 inline int grid_blocks(int per_sm) { return num_sms() * per_sm; }
 
@@ -584,39 +643,40 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 	}
 	s->table_entries = (size_t) s->cfg.gsize * s->cfg.gsize * s->cfg.gsize;
 	const size_t mb = (size_t) desc->max_blocks;
-	CK(cudaMalloc(&s->d_state, sizeof(StepState)));
+	CK(pool_alloc(&s->d_state, sizeof(StepState)));
 	CK(cudaMemsetAsync(s->d_state, 0, sizeof(StepState), s->stream));
 	CK(cudaMallocHost(&s->h_state, sizeof(StepState)));
 	memset(s->h_state, 0, sizeof(StepState));
 	for(int i = 0; i < 2; ++i) {
 		int e = alloc_partition(s, s->part[i]);
 		if(e) return e;
-		CK(cudaMalloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
+		// the next grid is exposed to the peers through CUDA IPC in MGSP mode: not pooled then
+		CK(s->desc.mgsp_world > 1 ? cudaMalloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)) : pool_alloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
 		CK(cudaMemsetAsync(s->grid[i], 0, (mb + 1) * kGridBlockFloats * sizeof(float), s->stream));
 	}
-	CK(cudaMalloc(&s->marks, (mb + 2) * sizeof(int)));
-	CK(cudaMalloc(&s->dest, (mb + 2) * sizeof(int)));
-	CK(cudaMalloc(&s->d_scratch, 16 * sizeof(int)));
+	CK(pool_alloc(&s->marks, (mb + 2) * sizeof(int)));
+	CK(pool_alloc(&s->dest, (mb + 2) * sizeof(int)));
+	CK(pool_alloc(&s->d_scratch, 16 * sizeof(int)));
 	CK(cudaMemsetAsync(s->d_scratch, 0, 16 * sizeof(int), s->stream));
 	if(s->desc.mgsp_world > 1) {
 		if(s->desc.mgsp_world > kMaxRanks || s->desc.mgsp_rank < 0 || s->desc.mgsp_rank >= s->desc.mgsp_world) return (int) cudaErrorInvalidValue;
 		if(s->desc.mgsp_halo_cap <= 0) s->desc.mgsp_halo_cap = desc->max_blocks / 2;
-		CK(cudaMalloc(&s->peer_overlap_keys, (size_t) s->desc.mgsp_world * mb * 3 * sizeof(int)));
-		CK(cudaMalloc(&s->peer_overlap_count, (size_t) s->desc.mgsp_world * sizeof(int)));
+		CK(pool_alloc(&s->peer_overlap_keys, (size_t) s->desc.mgsp_world * mb * 3 * sizeof(int)));
+		CK(pool_alloc(&s->peer_overlap_count, (size_t) s->desc.mgsp_world * sizeof(int)));
 		CK(cudaMemsetAsync(s->peer_overlap_count, 0, (size_t) s->desc.mgsp_world * sizeof(int), s->stream));
 		s->inbox_layout = make_inbox_layout(s->desc.mgsp_world, s->desc.mgsp_halo_cap, desc->max_blocks);
 		CK(cudaMalloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
 		CK(cudaMemsetAsync(s->inbox_local, 0, inbox_bytes(s->inbox_layout), s->stream));
 		s->inbox_peer[s->desc.mgsp_rank] = s->inbox_local;
 		s->grid1_peer[s->desc.mgsp_rank] = s->grid[1];
-		CK(cudaMalloc(&s->peer_bno, (size_t) s->desc.mgsp_world * mb * sizeof(int)));
+		CK(pool_alloc(&s->peer_bno, (size_t) s->desc.mgsp_world * mb * sizeof(int)));
 		CK(cudaMemsetAsync(s->peer_bno, 0xff, (size_t) s->desc.mgsp_world * mb * sizeof(int), s->stream));
-		CK(cudaMalloc(&s->mgsp_done, 16 * sizeof(int)));
+		CK(pool_alloc(&s->mgsp_done, 16 * sizeof(int)));
 		CK(cudaMemsetAsync(s->mgsp_done, 0, 16 * sizeof(int), s->stream));
 		s->mgsp_epochs = s->mgsp_done + 4;
 		for(int i = 0; i < 2; ++i) {
-			CK(cudaMalloc(&s->halo_list[i], (mb + 1) * sizeof(int)));
-			CK(cudaMalloc(&s->interior_list[i], (mb + 1) * sizeof(int)));
+			CK(pool_alloc(&s->halo_list[i], (mb + 1) * sizeof(int)));
+			CK(pool_alloc(&s->interior_list[i], (mb + 1) * sizeof(int)));
 			s->interior_count[i] = s->mgsp_done + 8 + i;
 		}
 		CK(cudaStreamSynchronize(s->stream));
@@ -635,38 +695,38 @@ int cb200_sim_destroy(cb200_sim* s) {
 	for(int i = 0; i < 2; ++i) {
 		if(s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
 		free_partition(s->part[i]);
-		cudaFree(s->grid[i]);
+		g_pool.release(s->grid[i]);
 	}
 	for(Model& m : s->models) {
 		for(int i = 0; i < 2; ++i) {
-			cudaFree(m.pb[i].bins);
-			cudaFree(m.pb[i].cell_particle_counts);
-			cudaFree(m.pb[i].particle_bucket_sizes);
-			cudaFree(m.pb[i].cellbuckets);
-			cudaFree(m.pb[i].blockbuckets);
-			cudaFree(m.pb[i].bin_offsets);
+			g_pool.release(m.pb[i].bins);
+			g_pool.release(m.pb[i].cell_particle_counts);
+			g_pool.release(m.pb[i].particle_bucket_sizes);
+			g_pool.release(m.pb[i].cellbuckets);
+			g_pool.release(m.pb[i].blockbuckets);
+			g_pool.release(m.pb[i].bin_offsets);
 		}
-		cudaFree(m.d_pos);
-		cudaFree(m.bin_sizes);
-		cudaFree(m.d_out);
+		g_pool.release(m.d_pos);
+		g_pool.release(m.bin_sizes);
+		g_pool.release(m.d_out);
 		cudaFreeHost(m.h_out);
 	}
-	cudaFree(s->marks);
-	cudaFree(s->dest);
-	cudaFree(s->d_scratch);
-	cudaFree(s->d_state);
-	cudaFree(s->peer_overlap_keys);
-	cudaFree(s->peer_overlap_count);
+	g_pool.release(s->marks);
+	g_pool.release(s->dest);
+	g_pool.release(s->d_scratch);
+	g_pool.release(s->d_state);
+	g_pool.release(s->peer_overlap_keys);
+	g_pool.release(s->peer_overlap_count);
 	for(int r = 0; r < kMaxRanks; ++r)
 		if(s->inbox_opened[r]) cudaIpcCloseMemHandle(s->inbox_peer[r]);
 	for(int r = 0; r < kMaxRanks; ++r)
 		if(s->grid1_opened[r]) cudaIpcCloseMemHandle(s->grid1_peer[r]);
-	cudaFree(s->peer_bno);
-	cudaFree(s->inbox_local);
-	cudaFree(s->mgsp_done);
+	g_pool.release(s->peer_bno);
+	g_pool.release(s->inbox_local);
+	g_pool.release(s->mgsp_done);
 	for(int i = 0; i < 2; ++i) {
-		cudaFree(s->halo_list[i]);
-		cudaFree(s->interior_list[i]);
+		g_pool.release(s->halo_list[i]);
+		g_pool.release(s->interior_list[i]);
 	}
 	cudaFreeHost(s->h_state);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
@@ -688,19 +748,19 @@ int cb200_sim_init_model(cb200_sim* s, int material, const float* positions_host
 		cb200_particle_buffer& pb = m.pb[i];
 		memset(&pb, 0, sizeof(pb));
 		default_material(s->desc.cfg, material, pb);
-		CK(cudaMalloc(&pb.bins, (size_t) m.bin_capacity * binf * sizeof(float)));
-		CK(cudaMalloc(&pb.cell_particle_counts, (mb + 1) * kBlockVol * sizeof(int)));
-		CK(cudaMalloc(&pb.particle_bucket_sizes, (mb + 2) * sizeof(int)));
-		CK(cudaMalloc(&pb.cellbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
-		CK(cudaMalloc(&pb.blockbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
-		CK(cudaMalloc(&pb.bin_offsets, (mb + 2) * sizeof(int)));
+		CK(pool_alloc(&pb.bins, (size_t) m.bin_capacity * binf * sizeof(float)));
+		CK(pool_alloc(&pb.cell_particle_counts, (mb + 1) * kBlockVol * sizeof(int)));
+		CK(pool_alloc(&pb.particle_bucket_sizes, (mb + 2) * sizeof(int)));
+		CK(pool_alloc(&pb.cellbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
+		CK(pool_alloc(&pb.blockbuckets, (mb + 1) * (size_t) s->cfg.ppb * sizeof(int)));
+		CK(pool_alloc(&pb.bin_offsets, (mb + 2) * sizeof(int)));
 		CK(cudaMemsetAsync(pb.cell_particle_counts, 0, (mb + 1) * kBlockVol * sizeof(int), s->stream));
 		CK(cudaMemsetAsync(pb.particle_bucket_sizes, 0, (mb + 2) * sizeof(int), s->stream));
 		CK(cudaMemsetAsync(pb.bin_offsets, 0, (mb + 2) * sizeof(int), s->stream));
 	}
-	CK(cudaMalloc(&m.bin_sizes, (mb + 2) * sizeof(int)));
+	CK(pool_alloc(&m.bin_sizes, (mb + 2) * sizeof(int)));
 	CK(cudaMemsetAsync(m.bin_sizes, 0, (mb + 2) * sizeof(int), s->stream));
-	CK(cudaMalloc(&m.d_pos, (size_t) n * 3 * sizeof(float)));
+	CK(pool_alloc(&m.d_pos, (size_t) n * 3 * sizeof(float)));
 	CK(cudaMemcpyAsync(m.d_pos, positions_host, (size_t) n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	if(model_id) *model_id = (int) s->models.size();
@@ -959,11 +1019,11 @@ static int retrieve_impl(cb200_sim* s, int model, float* host, int nch, int* n_o
 	const int R = s->rollid, Rn = R ^ 1;
 	const size_t need = (size_t) m.n * nch;
 	if(m.out_floats < need) {
-		cudaFree(m.d_out);
+		g_pool.release(m.d_out);
 		cudaFreeHost(m.h_out);
 		m.d_out = nullptr;
 		m.h_out = nullptr;
-		CK(cudaMalloc(&m.d_out, need * sizeof(float)));
+		CK(pool_alloc(&m.d_out, need * sizeof(float)));
 		m.out_floats = need;
 	}
 	if(!host && !m.h_out) CK(cudaMallocHost(&m.h_out, m.out_floats * sizeof(float)));
@@ -1007,6 +1067,10 @@ int cb200_sim_grid(cb200_sim* s, float* grid_host, int capacity_blocks, int* n_o
 	return 0;
 }
 long long cb200_sim_launch_count(cb200_sim* s) { return s ? s->launches : 0; }
+int cb200_trim_pool(void) {
+	g_pool.trim();
+	return 0;
+}
 
 // ---- MGSP peer wiring ------------------------------------------------------------------------------------------
 int cb200_sim_mgsp_inbox(cb200_sim* s, void** inbox, void** next_grid, size_t* inbox_bytes_out) {

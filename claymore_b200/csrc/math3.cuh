@@ -79,8 +79,13 @@ __device__ __forceinline__ void jacobi_rotate(float& a, float& b, float& c, floa
 template<int SWEEPS>
 __device__ __forceinline__ Quat jacobi_eigen_quat(Sym3 m) {
 	Quat q {1.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
 	for(int it = 0; it < SWEEPS; ++it) {
+		// converged: the off-diagonal is below FP32 resolution of the diagonal (further rotations would be identities).
+		// Nearly undeformed particles (sand at rest, elastic bodies in free flight) leave after zero or one sweep.
+		const float off = m.s21 * m.s21 + m.s31 * m.s31 + m.s32 * m.s32;
+		const float dia = m.s11 * m.s11 + m.s22 * m.s22 + m.s33 * m.s33;
+		if(off <= 1e-14f * dia) break;
 		jacobi_rotate(m.s11, m.s21, m.s22, m.s31, m.s32, m.s33, q.s, q.x, q.y, q.z);
 		jacobi_rotate(m.s22, m.s32, m.s33, m.s21, m.s31, m.s11, q.s, q.y, q.z, q.x);
 		jacobi_rotate(m.s33, m.s31, m.s11, m.s32, m.s21, m.s22, q.s, q.z, q.x, q.y);

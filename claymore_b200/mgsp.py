@@ -78,12 +78,13 @@ def bench_mgsp(args, scene, label, rank, world, local_rank):
     connect(sim, dist)
     sim.initial_setup()
     dist.barrier()
-    sim.step(args.warmup)
-    sim.sync()
-    assert sim.stats().error == 0, f"rank {rank}: engine error bits {sim.stats().error} after warm-up"
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        clocks.mark()
+    sim.step(args.warmup)
+    sim.sync()
+    assert sim.stats().error == 0, f"rank {rank}: engine error bits {sim.stats().error} after warm-up"
     l0 = sim.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()

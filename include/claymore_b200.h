@@ -76,6 +76,8 @@ typedef struct cb200_partition {
 } cb200_partition;
 
 CB200_API const char* cb200_version(void);
+/* device memory released by destroyed simulators is kept for re-use (per device, exact size); this returns it to the driver */
+CB200_API int cb200_trim_pool(void);
 CB200_API const char* cb200_error_string(int err);
 
 /* ------------------------------------------------------------------------------------------------
