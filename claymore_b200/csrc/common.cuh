@@ -194,6 +194,7 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // 128-bit streaming global accesses
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {

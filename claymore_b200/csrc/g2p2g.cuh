@@ -37,6 +37,15 @@ namespace cb200 {
 #ifndef CB200_G2P2G_MIN_CTAS
 #define CB200_G2P2G_MIN_CTAS 4  // measured on B200 (5M / 40M spheres): 2 CTAs/SM 6.4 / 7.0, 3: 7.7 / 8.5, 4: 8.4 / 9.3 G particle-steps/s;
 #endif                          // the kernel is latency bound (issue slots ~45 % busy), warps in flight beat spill-free registers
+#ifndef CB200_G2P2G_P2MAP
+#define CB200_G2P2G_P2MAP 1     // phase-2 thread map: 0 = (cell, slice) adjacent lanes, 1 = slice per warp pair (32 cells per warp)
+#endif
+#ifndef CB200_G2P2G_P2ROUNDS
+#define CB200_G2P2G_P2ROUNDS 1  // 1 (needs P2MAP 1): registers -> arena by plain adds in three rounds of plane-disjoint warps
+#endif
+#ifndef CB200_G2P2G_RECSWZ
+#define CB200_G2P2G_RECSWZ 1    // XOR-swizzle staged records: cell-major buckets put the p-th particles of consecutive cells 8 slots
+#endif                          // = 128 B apart, i.e. in the same four banks
 constexpr int kG2P2GThreads = CB200_G2P2G_THREADS;  // >= 192 = 64 cells x 3 stencil slices in phase 2
 static_assert(kG2P2GThreads >= 192 && kG2P2GThreads % 32 == 0, "phase 2 maps one thread to (cell, slice)");
 constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
@@ -90,10 +99,17 @@ struct G2P2GSmem {
 	int prevno[27];
 	int srcbin[27];
 	int nmovers;
-	int next_blk;
+	int cur_blk, next_blk;
 	unsigned long long bar;
 };
 
+__device__ __forceinline__ int rec_slot(int slot) {
+#if CB200_G2P2G_RECSWZ
+	return slot ^ ((slot >> 3) & 7);
+#else
+	return slot;
+#endif
+}
 constexpr int kRecMover = 1 << 30;
 constexpr int kRecDrop = 1 << 29;
 
@@ -136,15 +152,31 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 	const float dx = cfg.dx, dx_inv = cfg.dx_inv, d_inv = cfg.d_inv;
 	const int ppb_mask = cfg.ppb - 1;
 
-	// block queue: CTAs pull particle blocks from a device counter, so a launch that shares the SMs with another launch
-	// (MGSP: halo and interior blocks run concurrently on two streams) or starts late still balances
-	if(tid == 0) sm.next_blk = a.work_counter ? atomicAdd(a.work_counter, 1) : (int) blockIdx.x;
+	// block queue: CTAs pull particle blocks from a device counter, so a launch that shares the SMs with another launch or
+	// starts late still balances.  The queue runs TWO blocks ahead: thread 0 keeps the newest ticket in a register (the
+	// atomic's round trip hides behind a whole block) and every thread knows the next block (qn) while it works on this one.
+	int q_pending = 0;
+	if(tid == 0) {
+		if(a.work_counter) {
+			sm.next_blk = atomicAdd(a.work_counter, 1);
+			q_pending = atomicAdd(a.work_counter, 1);
+		} else {
+			sm.next_blk = (int) blockIdx.x;
+			q_pending = (int) (blockIdx.x + gridDim.x);
+		}
+		sm.cur_blk = nblocks;  // shifted in below
+	}
 	for(;;) {
 		__syncthreads();
-		const int qi = sm.next_blk;
+		if(tid == 0) {
+			sm.cur_blk = sm.next_blk;
+			sm.next_blk = q_pending;
+		}
 		__syncthreads();
+		const int qi = sm.cur_blk;
+		const int qn = sm.next_blk;
 		if(qi >= nblocks) break;
-		if(tid == 0) sm.next_blk = a.work_counter ? atomicAdd(a.work_counter, 1) : qi + (int) gridDim.x;
+		if(tid == 0) q_pending = a.work_counter ? atomicAdd(a.work_counter, 1) : qn + (int) gridDim.x;
 		const int blk = a.block_list ? a.block_list[qi] : qi;
 		int total_size = 0;
 		for(int mi = 0; mi < a.n_models; ++mi) total_size += a.m[mi].next.particle_bucket_sizes[blk];
@@ -173,7 +205,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			const int d = tid - 32;
 			const int ox = d / 9 - 1, oy = (d / 3) % 3 - 1, oz = d % 3 - 1;
 			sm.nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
-			sm.prevno[d] = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
+			const int pno = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
+			sm.prevno[d] = pno;
+			sm.srcbin[d] = pno >= 0 ? a.m[0].cur.bin_offsets[pno] : -1;
 		}
 		bool acc_dirty = true;  // the arena still feeds the previous block's bulk reductions: it is drained and zeroed just
 		                        // before this block's first accumulation, i.e. behind its whole phase 1
@@ -192,11 +226,13 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		const G2P2GModel& M = a.m[mi];
 		const int bucket_size = M.next.particle_bucket_sizes[blk];
 		if(bucket_size == 0) continue;
-		if(tid < 27) {
-			const int pno = sm.prevno[tid];
-			sm.srcbin[tid] = pno >= 0 ? M.cur.bin_offsets[pno] : -1;
+		if(mi > 0) {  // model 0's source bins were resolved with the neighbourhood
+			if(tid < 27) {
+				const int pno = sm.prevno[tid];
+				sm.srcbin[tid] = pno >= 0 ? M.cur.bin_offsets[pno] : -1;
+			}
+			__syncthreads();
 		}
-		__syncthreads();
 		const float mass = M.mat.mass;
 		const int dst_bin0 = M.next.bin_offsets[blk];
 		const int* __restrict__ bucket = M.next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
@@ -219,15 +255,17 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const float* __restrict__ sbin = M.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
 
 				float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
-				// the remaining channels are needed only after G2P: pull their lines into L1 now (no registers held)
-				if constexpr(MAT == CB200_J_FLUID) {
-					prefetch_l1(sbin + 96);
-				} else {
+				{
+					// the remaining channels are needed only after G2P: pull their lines into L1 now (no registers held)
+					if constexpr(MAT == CB200_J_FLUID) {
+						prefetch_l1(sbin + 96);
+					} else {
 #pragma unroll
-					for(int d = 0; d < 9; ++d) prefetch_l1(sbin + (3 + d) * 32);
-					if constexpr(MAT != CB200_FIXED_COROTATED) prefetch_l1(sbin + 12 * 32);
+						for(int d = 0; d < 9; ++d) prefetch_l1(sbin + (3 + d) * 32);
+						if constexpr(MAT != CB200_FIXED_COROTATED) prefetch_l1(sbin + 12 * 32);
+					}
+					if(slot + T < nchunk) prefetch_l1(bucket + pidib + T);
 				}
-				if(slot + T < nchunk) prefetch_l1(bucket + pidib + T);
 				int base[3], ab[3];
 				float lp[3], w[3][3];
 #pragma unroll
@@ -402,10 +440,11 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
 				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
 				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
-				sm.rec[0][slot] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
-				sm.rec[1][slot] = make_float4(q0, q1, q2, contrib[0] * dx);
-				sm.rec[2][slot] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
-				sm.rec[3][slot] = make_float4(contrib[5] * dx, contrib[6] * dx, contrib[7] * dx, contrib[8] * dx);
+				const int rs = rec_slot(slot);
+				sm.rec[0][rs] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
+				sm.rec[1][rs] = make_float4(q0, q1, q2, contrib[0] * dx);
+				sm.rec[2][rs] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
+				sm.rec[3][rs] = make_float4(contrib[5] * dx, contrib[6] * dx, contrib[7] * dx, contrib[8] * dx);
 				// counting sort by the cell the particle came from (its accumulation home)
 				const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
 				const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);
@@ -440,9 +479,16 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			__syncthreads();
 
 			// ================= phase 2: cell-parallel accumulation =====================================
-			if(tid < 192) {
-				const int hc = tid / 3, sl = tid - 3 * hc;
-				const int n = sm.cnt[hc], st = sm.start[hc];
+			// thread = (x-slice sl, home cell hc); warp w holds slice w/2 of the 32 cells of half w%2 (cell x = 2h, 2h+1)
+			{
+				const int wrp = tid >> 5;
+#if CB200_G2P2G_P2MAP
+				const int sl = wrp >> 1, hc = tid & 63;
+#else
+				const int hc = (tid / 3) & 63, sl = tid - 3 * (tid / 3);
+#endif
+				const bool p2 = tid < 192;
+				const int n = p2 ? sm.cnt[hc] : 0, st = p2 ? sm.start[hc] : 0;
 				float pa, pb, pc;
 				bspline_poly(sl, pa, pb, pc);
 				const float fi = (float) sl;
@@ -450,7 +496,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 #pragma unroll
 				for(int n9 = 0; n9 < 9; ++n9) acc[n9][0] = acc[n9][1] = acc[n9][2] = acc[n9][3] = 0.f;
 				for(int p = 0; p < n; ++p) {
-					const int slot = sm.idx[st + p];
+					const int slot = rec_slot(sm.idx[st + p]);
 					const float4 r0 = sm.rec[0][slot];
 					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
 					const float4 r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
@@ -474,9 +520,38 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						}
 					}
 				}
+				const int X = (hc >> 4) + 1 + sl, Y = ((hc >> 2) & 3) + 1, Z = (hc & 3) + 1;
+				const int ox = acc_off_x(X);
+#if CB200_G2P2G_P2ROUNDS
+				// Registers -> arena by plain read-add-write.  Within one warp all lanes execute the same stencil offset (j, k) on 32
+				// different cells, i.e. 32 different nodes; warp w touches the node planes X in {2h+sl+1, 2h+sl+2}, so the six warps
+				// go in three rounds of plane-disjoint warps: {w0, w1, w5}, {w2, w3}, {w4}.
+				static_assert(CB200_G2P2G_P2MAP == 1, "rounds need the slice-per-warp map");
+				const int my_round = wrp == 5 ? 0 : (wrp >> 1);  // threads >= 192 (wrp >= 6) never match
+#pragma unroll 1
+				for(int round = 0; round < 3; ++round) {
+					if(round == my_round && p2) {
+#pragma unroll
+						for(int j = 0; j < 3; ++j) {
+							const int oxy = ox + acc_off_y(Y + j);
+#pragma unroll
+							for(int k = 0; k < 3; ++k) {
+								const int o = oxy + acc_off_z(Z + k);
+								if(n > 0) {
+									const float m0 = sm.acc[o], m1 = sm.acc[o + 64], m2 = sm.acc[o + 128], m3 = sm.acc[o + 192];
+									sm.acc[o] = m0 + mass * acc[j * 3 + k][0];
+									sm.acc[o + 64] = m1 + acc[j * 3 + k][1];
+									sm.acc[o + 128] = m2 + acc[j * 3 + k][2];
+									sm.acc[o + 192] = m3 + acc[j * 3 + k][3];
+								}
+								__syncwarp();
+							}
+						}
+					}
+					__syncthreads();
+				}
+#else
 				if(n > 0) {
-					const int X = (hc >> 4) + 1 + sl, Y = ((hc >> 2) & 3) + 1, Z = (hc & 3) + 1;
-					const int ox = acc_off_x(X);
 #pragma unroll
 					for(int j = 0; j < 3; ++j) {
 						const int oxy = ox + acc_off_y(Y + j);
@@ -490,6 +565,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						}
 					}
 				}
+#endif
 			}
 			// ================= phase 3: particles that changed cell, node-parallel ====================
 			{
@@ -497,7 +573,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				for(int wk = tid; wk < total; wk += T) {
 					const int m = wk / 27, nn = wk - 27 * m;
 					const int i = nn / 9, j = (nn / 3) % 3, k = nn % 3;
-					const int slot = sm.movers[m];
+					const int slot = rec_slot(sm.movers[m]);
 					const float4 r0 = sm.rec[0][slot], r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
 					const int code = __float_as_int(r0.w);
 					float pa, pb, pc;
@@ -527,7 +603,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		fence_proxy_async();
 		__syncthreads();
 		if(tid < 8) {
-			const int bno = table_query(cfg, a.table, kx + ((tid >> 2) & 1), ky + ((tid >> 1) & 1), kz + (tid & 1));
+			const int bno = sm.nbr[(((tid >> 2) & 1) + 1) * 9 + (((tid >> 1) & 1) + 1) * 3 + (tid & 1) + 1];
 			if(bno >= 0) {
 				tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
 				if(a.overlap_marks) {
