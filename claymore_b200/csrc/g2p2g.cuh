@@ -37,15 +37,9 @@ namespace cb200 {
 #ifndef CB200_G2P2G_MIN_CTAS
 #define CB200_G2P2G_MIN_CTAS 4  // measured on B200 (5M / 40M spheres): 2 CTAs/SM 6.4 / 7.0, 3: 7.7 / 8.5, 4: 8.4 / 9.3 G particle-steps/s;
 #endif                          // the kernel is latency bound (issue slots ~45 % busy), warps in flight beat spill-free registers
-#ifndef CB200_G2P2G_P2MAP
-#define CB200_G2P2G_P2MAP 1     // phase-2 thread map: 0 = (cell, slice) adjacent lanes, 1 = slice per warp pair (32 cells per warp)
+#ifndef CB200_G2P2G_ROUNDS2
+#define CB200_G2P2G_ROUNDS2 1   // registers -> arena in 2 rounds (half-warp pairs of one node plane combined by shuffles) instead of 3
 #endif
-#ifndef CB200_G2P2G_P2ROUNDS
-#define CB200_G2P2G_P2ROUNDS 1  // 1 (needs P2MAP 1): registers -> arena by plain adds in three rounds of plane-disjoint warps
-#endif
-#ifndef CB200_G2P2G_RECSWZ
-#define CB200_G2P2G_RECSWZ 1    // XOR-swizzle staged records: cell-major buckets put the p-th particles of consecutive cells 8 slots
-#endif                          // = 128 B apart, i.e. in the same four banks
 constexpr int kG2P2GThreads = CB200_G2P2G_THREADS;  // >= 192 = 64 cells x 3 stencil slices in phase 2
 static_assert(kG2P2GThreads >= 192 && kG2P2GThreads % 32 == 0, "phase 2 maps one thread to (cell, slice)");
 constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
@@ -94,22 +88,18 @@ struct G2P2GSmem {
 	unsigned short idx[kChunk];      // staged slots sorted by cell
 	unsigned short movers[kChunk];   // staged slots of particles that changed cell
 	int cnt[64];
-	int start[65];
 	int nbr[27];
 	int prevno[27];
 	int srcbin[27];
 	int nmovers;
 	int cur_blk, next_blk;
+	unsigned valid;                  // bit b: grid block b of the 2x2x2 neighbourhood exists
 	unsigned long long bar;
 };
 
-__device__ __forceinline__ int rec_slot(int slot) {
-#if CB200_G2P2G_RECSWZ
-	return slot ^ ((slot >> 3) & 7);
-#else
-	return slot;
-#endif
-}
+// Staged records are XOR-swizzled: cell-major buckets put the p-th particles of consecutive cells 8 slots = 128 B apart,
+// i.e. in the same four banks; unswizzled, phase 2 spent 3-5 wavefronts per 16-byte read (profiles/r01_final_*).
+__device__ __forceinline__ int rec_slot(int slot) { return slot ^ ((slot >> 3) & 7); }
 constexpr int kRecMover = 1 << 30;
 constexpr int kRecDrop = 1 << 29;
 
@@ -153,92 +143,101 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 	const int ppb_mask = cfg.ppb - 1;
 
 	// block queue: CTAs pull particle blocks from a device counter, so a launch that shares the SMs with another launch or
-	// starts late still balances.  The queue runs TWO blocks ahead: thread 0 keeps the newest ticket in a register (the
-	// atomic's round trip hides behind a whole block) and every thread knows the next block (qn) while it works on this one.
+	// starts late still balances.  The queue runs two blocks ahead: thread 0 keeps the newest ticket in a register, so the
+	// atomic's round trip hides behind a whole block, and the queue shift rides on the flush barrier of the block before.
+	// Barriers per (single-chunk) block: S2, B1, B2, two or three for the arena rounds, B6.
 	int q_pending = 0;
 	if(tid == 0) {
 		if(a.work_counter) {
+			sm.cur_blk = atomicAdd(a.work_counter, 1);
 			sm.next_blk = atomicAdd(a.work_counter, 1);
-			q_pending = atomicAdd(a.work_counter, 1);
 		} else {
-			sm.next_blk = (int) blockIdx.x;
-			q_pending = (int) (blockIdx.x + gridDim.x);
+			sm.cur_blk = (int) blockIdx.x;
+			sm.next_blk = (int) (blockIdx.x + gridDim.x);
 		}
-		sm.cur_blk = nblocks;  // shifted in below
 	}
+	__syncthreads();
 	for(;;) {
-		__syncthreads();
-		if(tid == 0) {
-			sm.cur_blk = sm.next_blk;
-			sm.next_blk = q_pending;
-		}
-		__syncthreads();
-		const int qi = sm.cur_blk;
-		const int qn = sm.next_blk;
+		const int qi = sm.cur_blk, qn = sm.next_blk;  // published by the last barrier every thread passed
 		if(qi >= nblocks) break;
 		if(tid == 0) q_pending = a.work_counter ? atomicAdd(a.work_counter, 1) : qn + (int) gridDim.x;
 		const int blk = a.block_list ? a.block_list[qi] : qi;
 		int total_size = 0;
 		for(int mi = 0; mi < a.n_models; ++mi) total_size += a.m[mi].next.particle_bucket_sizes[blk];
-		if(total_size == 0) continue;
-		if(a.halo_mode && !a.block_list) {
-			const bool is_halo = a.halo_marks[blk] != 0;
-			if((a.halo_mode == 1) != is_halo) continue;
+		bool skip = total_size == 0;
+		if(a.halo_mode && !a.block_list) skip |= (a.halo_mode == 1) != (a.halo_marks[blk] != 0);
+		if(skip) {
+			__syncthreads();
+			if(tid == 0) {
+				sm.cur_blk = qn;
+				sm.next_blk = q_pending;
+			}
+			__syncthreads();
+			continue;
 		}
 		const int kx = a.keys[3 * blk], ky = a.keys[3 * blk + 1], kz = a.keys[3 * blk + 2];
 
 		// ---- stage the neighbourhood -------------------------------------------------------------
+		// (the landing zone aliases the records of the previous block: its last readers are behind that block's B6)
 		if(tid < 32) {
 			const int lb = tid & 7;
 			const int bno = table_query(cfg, a.table, kx + ((lb >> 2) & 1), ky + ((lb >> 1) & 1), kz + (lb & 1));
 			const unsigned valid = __ballot_sync(0xffffffffu, tid < 8 && bno >= 0);
-			if(tid == 0) mbar_arrive_expect_tx(bar, __popc(valid) * 768);
-			__syncwarp();
-			if(tid < 8) {
-				if(bno >= 0) {
-					tma_load_1d(velsoa + lb * 192, a.grid + (size_t) bno * kGridBlockFloats + 64, 768, bar);
-				} else {
-					for(int i = 0; i < 192; ++i) velsoa[lb * 192 + i] = 0.f;
-				}
+			if(tid == 0) {
+				sm.valid = valid;  // released by the arrive, acquired by every thread's wait
+				mbar_arrive_expect_tx(bar, __popc(valid) * 768);
 			}
+			__syncwarp();
+			if(tid < 8 && bno >= 0) tma_load_1d(velsoa + lb * 192, a.grid + (size_t) bno * kGridBlockFloats + 64, 768, bar);
 		} else if(tid < 32 + 27) {
 			const int d = tid - 32;
 			const int ox = d / 9 - 1, oy = (d / 3) % 3 - 1, oz = d % 3 - 1;
 			sm.nbr[d] = table_query(cfg, a.table, kx + ox, ky + oy, kz + oz);
 			const int pno = table_query(cfg, a.prev_table, kx + ox, ky + oy, kz + oz);
 			sm.prevno[d] = pno;
-			sm.srcbin[d] = pno >= 0 ? a.m[0].cur.bin_offsets[pno] : -1;
+			sm.srcbin[d] = pno >= 0 ? a.m[0].cur.bin_offsets[pno] : -1;  // model 0; further models resolve theirs below
 		}
 		bool acc_dirty = true;  // the arena still feeds the previous block's bulk reductions: it is drained and zeroed just
 		                        // before this block's first accumulation, i.e. behind its whole phase 1
-		__syncthreads();
 		mbar_wait(bar, phase);
 		phase ^= 1;
-		// SoA landing zone -> one float4 per node
-		for(int n = tid; n < 512; n += T) {
-			const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
-			const int o = (((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2)) * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
-			sm.vel4[n] = make_float4(velsoa[o], velsoa[o + 64], velsoa[o + 128], 0.f);
+		// SoA landing zone -> one float4 per node (zero where the grid block does not exist)
+		{
+			const unsigned valid = sm.valid;
+			for(int n = tid; n < 512; n += T) {
+				const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
+				const int bi = ((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2);
+				const int o = bi * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
+				sm.vel4[n] = ((valid >> bi) & 1u) ? make_float4(velsoa[o], velsoa[o + 64], velsoa[o + 128], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
 		}
-		__syncthreads();
+		__syncthreads();  // S2: vel4, nbr, prevno, srcbin
 
+		bool first_chunk = true;
 		for(int mi = 0; mi < a.n_models; ++mi) {
 		const G2P2GModel& M = a.m[mi];
 		const int bucket_size = M.next.particle_bucket_sizes[blk];
 		if(bucket_size == 0) continue;
-		if(mi > 0) {  // model 0's source bins were resolved with the neighbourhood
-			if(tid < 27) {
-				const int pno = sm.prevno[tid];
-				sm.srcbin[tid] = pno >= 0 ? M.cur.bin_offsets[pno] : -1;
-			}
-			__syncthreads();
-		}
 		const float mass = M.mat.mass;
 		const int dst_bin0 = M.next.bin_offsets[blk];
 		const int* __restrict__ bucket = M.next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
 
 		for(int c0 = 0; c0 < bucket_size; c0 += kChunk) {
 			const int nchunk = min(kChunk, bucket_size - c0);
+			{
+				// every chunk after the first of a block waits for the previous one's phase 3; a further model resolves its bins
+				const bool need_srcbin = mi > 0 && c0 == 0;
+				if(!first_chunk || need_srcbin) {
+					if(!first_chunk) __syncthreads();
+					if(!first_chunk && tid == 0) sm.nmovers = 0;
+					if(need_srcbin && tid < 27) {
+						const int pno = sm.prevno[tid];
+						sm.srcbin[tid] = pno >= 0 ? M.cur.bin_offsets[pno] : -1;
+					}
+					__syncthreads();
+				}
+				first_chunk = false;
+			}
 			int cr0 = -1, cr1 = -1, cr2 = -1;  // (home cell << 16) | rank of the up-to-three particles of this thread
 			static_assert(ITERS <= 3, "cellrank registers");
 
@@ -453,42 +452,55 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				else cr2 = cr;
 			}
 			if(acc_dirty && tid < 8) tma_wait_read<0>();  // the TMA unit has read the arena of the previous block
-			__syncthreads();
+			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete
 			if(acc_dirty) {
 				float4* acc4 = reinterpret_cast<float4*>(sm.acc);
 				for(int i = tid; i < 8 * 256 / 4; i += T) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 				acc_dirty = false;
 			}
-			if(tid < 32) {
-				const int c0v = sm.cnt[2 * tid], c1v = sm.cnt[2 * tid + 1];
-				const int pair = c0v + c1v;
-				int inc = pair;
+			// exclusive scan of the 64 cell counts, redundantly in every warp (lane l holds cells 2l and 2l+1): no barrier,
+			// no shared prefix array
+			const int lane = tid & 31;
+			const int c0v = sm.cnt[2 * lane], c1v = sm.cnt[2 * lane + 1];
+			int excl = c0v + c1v;
 #pragma unroll
-				for(int o = 1; o < 32; o <<= 1) {
-					const int t = __shfl_up_sync(0xffffffffu, inc, o);
-					if(tid >= o) inc += t;
-				}
-				sm.start[2 * tid] = inc - pair;
-				sm.start[2 * tid + 1] = inc - pair + c0v;
-				if(tid == 31) sm.start[64] = inc;
+			for(int o = 1; o < 32; o <<= 1) {
+				const int t = __shfl_up_sync(0xffffffffu, excl, o);
+				if(lane >= o) excl += t;
 			}
-			__syncthreads();
-			if(cr0 >= 0) sm.idx[sm.start[cr0 >> 16] + (cr0 & 0xffff)] = (unsigned short) tid;
-			if(cr1 >= 0) sm.idx[sm.start[cr1 >> 16] + (cr1 & 0xffff)] = (unsigned short) (T + tid);
-			if(cr2 >= 0) sm.idx[sm.start[cr2 >> 16] + (cr2 & 0xffff)] = (unsigned short) (2 * T + tid);
-			__syncthreads();
+			excl -= c0v + c1v;
+			auto cell_start = [&](int h) {  // every lane of the warp must call it
+				const int e = __shfl_sync(0xffffffffu, excl, h >> 1), c = __shfl_sync(0xffffffffu, c0v, h >> 1);
+				return e + ((h & 1) ? c : 0);
+			};
+			{
+				const int s0 = cell_start(max(cr0, 0) >> 16), s1 = cell_start(max(cr1, 0) >> 16), s2 = cell_start(max(cr2, 0) >> 16);
+				if(cr0 >= 0) sm.idx[s0 + (cr0 & 0xffff)] = (unsigned short) tid;
+				if(cr1 >= 0) sm.idx[s1 + (cr1 & 0xffff)] = (unsigned short) (T + tid);
+				if(cr2 >= 0) sm.idx[s2 + (cr2 & 0xffff)] = (unsigned short) (2 * T + tid);
+			}
 
 			// ================= phase 2: cell-parallel accumulation =====================================
-			// thread = (x-slice sl, home cell hc); warp w holds slice w/2 of the 32 cells of half w%2 (cell x = 2h, 2h+1)
-			{
-				const int wrp = tid >> 5;
-#if CB200_G2P2G_P2MAP
-				const int sl = wrp >> 1, hc = tid & 63;
+			// thread = (home cell hc, x-slice sl of its 3x3x3 stencil); a half-warp holds the 16 cells of one x-plane
+			const int wrp = tid >> 5;
+			const bool p2 = tid < 192;
+#if CB200_G2P2G_ROUNDS2
+			// warp: (cx, sl) of lanes 0-15 / lanes 16-31 -> node plane X = cx + sl + 1
+			//   w0: (1,0) (0,1) -> 2 2    w1: (2,0) (1,1) -> 3 3    w2: (3,0) (2,1) -> 4 4    w3: (3,1) (2,2) -> 5 5
+			//   w4: (0,0) (3,2) -> 1 6    w5: (0,2) (1,2) -> 3 4
+			const int hi = lane >> 4;
+			const int cx = wrp < 3 ? wrp + 1 - hi : (wrp == 3 ? 3 - hi : (wrp == 4 ? 3 * hi : hi));
+			const int sl = wrp < 3 ? hi : (wrp == 3 ? 1 + hi : (wrp == 4 ? 2 * hi : 2));
+			const int hc = ((cx & 3) << 4) | (lane & 15);
 #else
-				const int hc = (tid / 3) & 63, sl = tid - 3 * (tid / 3);
+			// warp w: slice w/2 of the 32 cells with x in {2(w%2), 2(w%2)+1}
+			const int sl = wrp >> 1, hc = tid & 63;
 #endif
-				const bool p2 = tid < 192;
-				const int n = p2 ? sm.cnt[hc] : 0, st = p2 ? sm.start[hc] : 0;
+			const int n = p2 ? sm.cnt[hc] : 0;
+			const int st = cell_start(hc);
+			__syncthreads();  // B2: idx complete, every warp has read the cell counts
+			if(tid < 64) sm.cnt[tid] = 0;  // for the next chunk / block (ordered by the barriers below)
+			{
 				float pa, pb, pc;
 				bspline_poly(sl, pa, pb, pc);
 				const float fi = (float) sl;
@@ -520,13 +532,49 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						}
 					}
 				}
+				// Registers -> arena by plain read-add-write, no atomics (a shared float atomicAdd is a compare-and-swap loop: 36 per
+				// thread were 60 % of the kernel's shared-memory wavefronts).  All lanes of a warp execute the same stencil offset
+				// (j, k) on different cells, i.e. on different nodes, and a thread only writes the node plane X of its slice, so
+				// warps (half-warps) that own different planes never meet; the rest is ordered by rounds.
 				const int X = (hc >> 4) + 1 + sl, Y = ((hc >> 2) & 3) + 1, Z = (hc & 3) + 1;
 				const int ox = acc_off_x(X);
-#if CB200_G2P2G_P2ROUNDS
-				// Registers -> arena by plain read-add-write.  Within one warp all lanes execute the same stencil offset (j, k) on 32
-				// different cells, i.e. 32 different nodes; warp w touches the node planes X in {2h+sl+1, 2h+sl+2}, so the six warps
-				// go in three rounds of plane-disjoint warps: {w0, w1, w5}, {w2, w3}, {w4}.
-				static_assert(CB200_G2P2G_P2MAP == 1, "rounds need the slice-per-warp map");
+#if CB200_G2P2G_ROUNDS2
+				// round 0: w0-w3 (both halves hold the same plane: exchange by shuffle, lanes 0-15 add channels 0-1, lanes 16-31
+				// channels 2-3) and w4 (planes 1 and 6, all four channels per lane); round 1: w5 (planes 3 and 4)
+#pragma unroll 1
+				for(int round = 0; round < 2; ++round) {
+					if(p2 && round == (wrp == 5)) {
+						const bool pair = wrp < 4;
+#pragma unroll
+						for(int j = 0; j < 3; ++j) {
+							const int oxy = ox + acc_off_y(Y + j);
+#pragma unroll
+							for(int k = 0; k < 3; ++k) {
+								const int o = oxy + acc_off_z(Z + k);
+								const float v0 = mass * acc[j * 3 + k][0], v1 = acc[j * 3 + k][1], v2 = acc[j * 3 + k][2], v3 = acc[j * 3 + k][3];
+								if(pair) {
+									// partner = same (cy, cz), the other (cx, sl) of this plane: same node
+									const float ra = __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 16), rb = __shfl_xor_sync(0xffffffffu, hi ? v1 : v3, 16);
+									const int oc = o + (hi ? 128 : 0);
+									const float sa = (hi ? v2 : v0) + ra, sb = (hi ? v3 : v1) + rb;
+									const float m0 = sm.acc[oc], m1 = sm.acc[oc + 64];
+									sm.acc[oc] = m0 + sa;
+									sm.acc[oc + 64] = m1 + sb;
+								} else if(n > 0) {
+									const float m0 = sm.acc[o], m1 = sm.acc[o + 64], m2 = sm.acc[o + 128], m3 = sm.acc[o + 192];
+									sm.acc[o] = m0 + v0;
+									sm.acc[o + 64] = m1 + v1;
+									sm.acc[o + 128] = m2 + v2;
+									sm.acc[o + 192] = m3 + v3;
+								}
+								__syncwarp();
+							}
+						}
+					}
+					__syncthreads();
+				}
+#else
+				// warp w touches the planes {2h+sl+1, 2h+sl+2}: three rounds of plane-disjoint warps {w0, w1, w5}, {w2, w3}, {w4}
 				const int my_round = wrp == 5 ? 0 : (wrp >> 1);  // threads >= 192 (wrp >= 6) never match
 #pragma unroll 1
 				for(int round = 0; round < 3; ++round) {
@@ -549,21 +597,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						}
 					}
 					__syncthreads();
-				}
-#else
-				if(n > 0) {
-#pragma unroll
-					for(int j = 0; j < 3; ++j) {
-						const int oxy = ox + acc_off_y(Y + j);
-#pragma unroll
-						for(int k = 0; k < 3; ++k) {
-							const int o = oxy + acc_off_z(Z + k);
-							atomicAdd(&sm.acc[o], mass * acc[j * 3 + k][0]);
-							atomicAdd(&sm.acc[o + 64], acc[j * 3 + k][1]);
-							atomicAdd(&sm.acc[o + 128], acc[j * 3 + k][2]);
-							atomicAdd(&sm.acc[o + 192], acc[j * 3 + k][3]);
-						}
-					}
 				}
 #endif
 			}
@@ -592,18 +625,20 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					atomicAdd(&sm.acc[o + 192], W * (r1.z + fi * r2.y + fj * r3.x + fk * r3.w));
 				}
 			}
-			__syncthreads();
-			if(tid < 64) sm.cnt[tid] = 0;
-			if(tid == 64) sm.nmovers = 0;
-			__syncthreads();
 		}
 		}  // models
 
 		// ---- arena -> next grid: eight 1-KiB bulk add-reductions ----------------------------------
+		const int flush_bno = tid < 8 ? sm.nbr[(((tid >> 2) & 1) + 1) * 9 + (((tid >> 1) & 1) + 1) * 3 + (tid & 1) + 1] : -1;
 		fence_proxy_async();
-		__syncthreads();
+		if(tid == 0) {  // queue shift: every thread read cur/next at the top of this block, barriers ago
+			sm.cur_blk = qn;
+			sm.next_blk = q_pending;
+		}
+		__syncthreads();  // B6: arena, records and neighbour tables of this block are no longer written or read by the SM
+		if(tid == 0) sm.nmovers = 0;
 		if(tid < 8) {
-			const int bno = sm.nbr[(((tid >> 2) & 1) + 1) * 9 + (((tid >> 1) & 1) + 1) * 3 + (tid & 1) + 1];
+			const int bno = flush_bno;
 			if(bno >= 0) {
 				tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
 				if(a.overlap_marks) {
