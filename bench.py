@@ -243,6 +243,7 @@ def run_b200(args):
     sim.profile(True)
     sim.step(args.steps)
     g2p2g_ms, g2p2g_launches = sim.profile_read()
+    phases_ms = {k: round(v / args.steps, 4) for k, v in sim.profile_phases().items()}  # ungraphed pass, event per phase
     sim.profile(False)
     clk = clocks.stop()
     st = sim.stats()
@@ -313,6 +314,7 @@ def run_b200(args):
         "config": {"workload": label, "particles": n_particles, "particle_blocks": pbc, "dt": args.dt, "l2": "inputs larger than L2 (particle bins >= 500 MB)",
                    "graph": not args.no_graph},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        "phases_ms": phases_ms,
     }
     print(json.dumps(out))
 

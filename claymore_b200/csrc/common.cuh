@@ -193,6 +193,12 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 // make generic-proxy smem writes visible to the async proxy before a bulk store/reduce reads them
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Ampere-style asynchronous 4-byte copy global -> shared (LDGSTS): no destination register, completion by group
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

@@ -37,6 +37,9 @@ namespace cb200 {
 #ifndef CB200_G2P2G_MIN_CTAS
 #define CB200_G2P2G_MIN_CTAS 4  // measured on B200 (5M / 40M spheres): 2 CTAs/SM 6.4 / 7.0, 3: 7.7 / 8.5, 4: 8.4 / 9.3 G particle-steps/s;
 #endif                          // the kernel is latency bound (issue slots ~45 % busy), warps in flight beat spill-free registers
+#ifndef CB200_G2P2G_ASYNC
+#define CB200_G2P2G_ASYNC 1     // particle gathers by cp.async into the particle's own (not yet written) record slot
+#endif
 #ifndef CB200_G2P2G_ROUNDS2
 #define CB200_G2P2G_ROUNDS2 1   // registers -> arena in 2 rounds (half-warp pairs of one node plane combined by shuffles) instead of 3
 #endif
@@ -176,6 +179,18 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			continue;
 		}
 		const int kx = a.keys[3 * blk], ky = a.keys[3 * blk + 1], kz = a.keys[3 * blk + 2];
+#if CB200_G2P2G_ASYNC
+		// Gather tags of the first chunk: copied asynchronously into the unused w components of the velocity arena (512 words
+		// for 512 staged particles) while the neighbourhood is staged.  Thread t fetches the tags it will consume itself.
+		{
+			const int size0 = min(a.m[0].next.particle_bucket_sizes[blk], kChunk);
+			const int* bucket0 = a.m[0].next.blockbuckets + ((size_t) blk << cfg.ppb_shift);
+#pragma unroll
+			for(int it = 0; it < ITERS; ++it)
+				if(it * T + tid < size0) cp_async4(&sm.vel4[it * T + tid].w, bucket0 + it * T + tid);
+			cp_async_commit();
+		}
+#endif
 
 		// ---- stage the neighbourhood -------------------------------------------------------------
 		// (the landing zone aliases the records of the previous block: its last readers are behind that block's B6)
@@ -208,7 +223,13 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
 				const int bi = ((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2);
 				const int o = bi * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
+#if CB200_G2P2G_ASYNC
+				const bool ok = (valid >> bi) & 1u;  // w holds a gather tag in flight: write x, y, z only
+				*reinterpret_cast<float2*>(&sm.vel4[n].x) = ok ? make_float2(velsoa[o], velsoa[o + 64]) : make_float2(0.f, 0.f);
+				sm.vel4[n].z = ok ? velsoa[o + 128] : 0.f;
+#else
 				sm.vel4[n] = ((valid >> bi) & 1u) ? make_float4(velsoa[o], velsoa[o + 64], velsoa[o + 128], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
 			}
 		}
 		__syncthreads();  // S2: vel4, nbr, prevno, srcbin
@@ -238,6 +259,33 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				}
 				first_chunk = false;
 			}
+#if CB200_G2P2G_ASYNC
+			// Software pipeline of the gathers (no registers held, no reliance on the few KB of L1 left beside 208 KB of shared
+			// memory): tags sit in vel4[].w; the position of particle `slot` is copied into rec[0][slot] and its F / J / logJp into
+			// rec[1..3][slot] -- the particle's own record slot, which is written only at the end of its iteration.  Positions
+			// run one iteration ahead, F is in flight during G2P.
+			if(!(mi == 0 && c0 == 0)) {
+#pragma unroll
+				for(int it = 0; it < ITERS; ++it)
+					if(it * T + tid < nchunk) cp_async4(&sm.vel4[it * T + tid].w, bucket + c0 + it * T + tid);
+				cp_async_commit();
+			}
+			cp_async_wait<0>();
+			auto src_of = [&](int slot) {
+				const int tag = __float_as_int(sm.vel4[slot].w);
+				const int sp = tag & ppb_mask;
+				return M.cur.bins + ((size_t) sm.srcbin[tag >> cfg.ppb_shift] + (sp >> 5)) * BINF + (sp & 31);
+			};
+			auto fetch_pos = [&](int slot) {
+				const float* sb = src_of(slot);
+				float* dst = &sm.rec[0][rec_slot(slot)].x;
+				cp_async4(dst, sb);
+				cp_async4(dst + 1, sb + 32);
+				cp_async4(dst + 2, sb + 64);
+			};
+			if(tid < nchunk) fetch_pos(tid);
+			cp_async_commit();
+#endif
 			int cr0 = -1, cr1 = -1, cr2 = -1;  // (home cell << 16) | rank of the up-to-three particles of this thread
 			static_assert(ITERS <= 3, "cellrank registers");
 
@@ -247,6 +295,36 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int slot = it * T + tid;
 				if(slot >= nchunk) continue;
 				const int pidib = c0 + slot;
+#if CB200_G2P2G_ASYNC
+				const int rs = rec_slot(slot);
+				const float* __restrict__ sbin = src_of(slot);
+				{  // group A: the channels needed after G2P
+					float* dst = &sm.rec[1][rs].x;
+					if constexpr(MAT == CB200_J_FLUID) {
+						cp_async4(dst, sbin + 96);
+					} else {
+#pragma unroll
+						for(int d = 0; d < 4; ++d) cp_async4(dst + d, sbin + (3 + d) * 32);
+						dst = &sm.rec[2][rs].x;
+#pragma unroll
+						for(int d = 0; d < 4; ++d) cp_async4(dst + d, sbin + (7 + d) * 32);
+						dst = &sm.rec[3][rs].x;
+						cp_async4(dst, sbin + 11 * 32);
+						if constexpr(MAT != CB200_FIXED_COROTATED) cp_async4(dst + 1, sbin + 12 * 32);
+					}
+					cp_async_commit();
+				}
+				cp_async_wait<1>();  // everything but group A: this particle's position has landed
+				float pos[3];
+				{
+					const float4 p4 = sm.rec[0][rs];
+					pos[0] = p4.x;
+					pos[1] = p4.y;
+					pos[2] = p4.z;
+				}
+				if(slot + T < nchunk) fetch_pos(slot + T);  // group B: next particle's position, a whole iteration ahead
+				cp_async_commit();
+#else
 				const int advect = __ldg(bucket + pidib);
 				const int dir = advect >> cfg.ppb_shift;
 				const int src_pidib = advect & ppb_mask;
@@ -265,6 +343,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					}
 					if(slot + T < nchunk) prefetch_l1(bucket + pidib + T);
 				}
+#endif
 				int base[3], ab[3];
 				float lp[3], w[3][3];
 #pragma unroll
@@ -357,7 +436,12 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				float contrib[9];
 				float* __restrict__ dbin = M.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
 				if constexpr(MAT == CB200_J_FLUID) {
+#if CB200_G2P2G_ASYNC
+					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
+					float J = sm.rec[1][rs].x;
+#else
 					float J = __ldg(sbin + 96);
+#endif
 					J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
 					if(J < 0.1f) J = 0.1f;
 					const float voln = J * M.mat.volume;
@@ -378,8 +462,14 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					dbin[96] = J;
 				} else {
 					float Fo[9], F[9], G[9];
+#if CB200_G2P2G_ASYNC
+					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
+					const float4 fa = sm.rec[1][rs], fb = sm.rec[2][rs], fc = sm.rec[3][rs];
+					Fo[0] = fa.x, Fo[1] = fa.y, Fo[2] = fa.z, Fo[3] = fa.w, Fo[4] = fb.x, Fo[5] = fb.y, Fo[6] = fb.z, Fo[7] = fb.w, Fo[8] = fc.x;
+#else
 #pragma unroll
 					for(int d = 0; d < 9; ++d) Fo[d] = __ldg(sbin + (3 + d) * 32);
+#endif
 					const float sc = dt * d_inv;
 #pragma unroll
 					for(int d = 0; d < 9; ++d) G[d] = A[d] * sc + ((d & 3) ? 0.f : 1.f);
@@ -395,7 +485,11 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
 						stress_fixed_corotated_polar(M.mat, F, contrib);
 					} else {
+#if CB200_G2P2G_ASYNC
+						float log_jp = fc.y;
+#else
 						float log_jp = __ldg(sbin + 12 * 32);
+#endif
 						if constexpr(MAT == CB200_SAND) stress_sand(M.mat, F, contrib, log_jp);
 						else stress_nacc(M.mat, F, contrib, log_jp);
 #pragma unroll
@@ -439,7 +533,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
 				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
 				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
+#if !CB200_G2P2G_ASYNC
 				const int rs = rec_slot(slot);
+#endif
 				sm.rec[0][rs] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
 				sm.rec[1][rs] = make_float4(q0, q1, q2, contrib[0] * dx);
 				sm.rec[2][rs] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
@@ -451,6 +547,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				else if(it == 1) cr1 = cr;
 				else cr2 = cr;
 			}
+#if CB200_G2P2G_ASYNC
+			cp_async_wait<0>();
+#endif
 			if(acc_dirty && tid < 8) tma_wait_read<0>();  // the TMA unit has read the arena of the previous block
 			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete
 			if(acc_dirty) {
