@@ -112,6 +112,7 @@ struct StepState {
 	int bin_count[kMaxModels];
 	int halo_count;
 	long long steps;
+	int done_counter;       // CTAs of a launch that have finished ("last CTA does the epilogue"; zero between launches)
 };
 
 enum : int { kErrBlockCapacity = 1, kErrBinCapacity = 2, kErrLostParticle = 4, kErrCellOverflow = 8 };

@@ -140,8 +140,8 @@ struct cb200_sim {
 	StepState* h_state = nullptr;  // pinned
 	cb200_partition part[2];
 	float* grid[2] = {nullptr, nullptr};
-	int* marks = nullptr;
-	int* dest = nullptr;
+	int* tile_sums = nullptr;     // [tiles + 1][kScanComps] of summary_kernel / rebuild_kernel
+	int* block_totals = nullptr;  // [kMaxModels][max_blocks] particles per old block
 	int* d_scratch = nullptr;  // [0] new_pbc, [1] new_nbc snapshot, [2] parcount
 	std::vector<Model> models;
 	int rollid = 0;
@@ -312,6 +312,7 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 	const int Rn = R ^ 1;
 	const int nm = (int) s->models.size();
 	cudaStream_t st = s->stream;
+	const int tiles = (s->desc.max_blocks + kRebuildTile - 1) / kRebuildTile;
 	{
 		SummaryArgs a {};
 		a.cfg = s->cfg;
@@ -319,28 +320,16 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 		a.n_models = nm;
 		for(int m = 0; m < nm; ++m) {
 			a.cell_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
-			a.bucket_sizes[m] = s->models[m].pb[Rn].particle_bucket_sizes;
+			a.bin_offsets[m] = s->models[m].pb[R].bin_offsets;
 		}
-		a.marks = s->marks;
+		a.block_totals = s->block_totals;
+		a.tile_sums = s->tile_sums;
+		a.max_blocks = s->desc.max_blocks;
 		a.stale_table = s->part[Rn].index_table;
 		a.stale_keys = s->part[Rn].active_keys;
 		a.stale_count = s->part[Rn].count;
-		a.capacity = s->desc.max_blocks;
-		block_summary_kernel<<<grid_blocks(4), 256, 0, st>>>(a);
-		++s->launches;
-	}
-	{
-		ScanArgs a {};
-		a.count = count_dev(&s->d_state->ebc);
-		a.count_plus = 1;
-		a.in = s->marks;
-		a.out = s->dest;
-		a.total_out = s->d_scratch + 0;
-		a.total_out2 = s->part[Rn].count;
-		a.limit = s->desc.max_blocks;
-		a.error = &s->d_state->error;
-		a.error_bit = kErrBlockCapacity;
-		scan_kernel<<<1, 1024, 0, st>>>(a);
+		a.new_pbc = s->d_scratch + 0;
+		summary_kernel<<<tiles, kSummaryThreads, 0, st>>>(a);
 		++s->launches;
 	}
 	{
@@ -348,32 +337,20 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 		a.cfg = s->cfg;
 		a.state = s->d_state;
 		a.n_models = nm;
-		a.marks = s->marks;
-		a.dest = s->dest;
 		a.old_keys = s->part[R].active_keys;
 		a.new_keys = s->part[Rn].active_keys;
 		a.new_table = s->part[Rn].index_table;
+		a.block_totals = s->block_totals;
+		a.tile_sums = s->tile_sums;
+		a.max_blocks = s->desc.max_blocks;
 		for(int m = 0; m < nm; ++m) {
 			a.cell_counts[m] = s->models[m].pb[Rn].cell_particle_counts;
 			a.cellbuckets[m] = s->models[m].pb[Rn].cellbuckets;
 			a.dst_sizes[m] = s->models[m].pb[R].particle_bucket_sizes;
 			a.dst_buckets[m] = s->models[m].pb[R].blockbuckets;
-			a.bin_sizes[m] = s->models[m].bin_sizes;
+			a.bin_offsets[m] = s->models[m].pb[R].bin_offsets;
 		}
-		rebuild_kernel<<<grid_blocks(8), 256, 0, st>>>(a);
-		++s->launches;
-	}
-	{
-		ScanBatch b {};
-		for(int m = 0; m < nm; ++m) {
-			ScanArgs& a = b.a[m];
-			a.count = count_dev(s->d_scratch + 0);
-			a.count_plus = 1;
-			a.in = s->models[m].bin_sizes;
-			a.out = s->models[m].pb[R].bin_offsets;
-			a.total_out = &s->d_state->bin_count[m];
-		}
-		scan_batch_kernel<<<nm, 1024, 0, st>>>(b);
+		rebuild_kernel<<<tiles, kRebuildThreads, 0, st>>>(a);
 		++s->launches;
 	}
 	{
@@ -387,6 +364,8 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 		a.error = &s->d_state->error;
 		a.lo = 0;
 		a.span = 2;
+		a.done_counter = &s->d_state->done_counter;  // the last CTA snapshots the neighbour count
+		a.snapshot_out = s->d_scratch + 1;
 		register_blocks_kernel<<<grid_blocks(4), 128, 0, st>>>(a);
 		++s->launches;
 	}
@@ -408,8 +387,6 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 	const bool mgsp = s->desc.mgsp_world > 1;
 	float* local_max = reinterpret_cast<float*>(s->d_scratch + 3);
 	float* global_max = reinterpret_cast<float*>(s->d_scratch + 4);
-	snapshot_int_kernel<<<1, 32, 0, st>>>(s->part[Rn].count, s->d_scratch + 1);
-	++s->launches;
 	if(mgsp) {
 		CK(cudaMemsetAsync(local_max, 0, sizeof(float), st));
 		CK(enqueue_halo_tag_reset(s, Rn));
@@ -432,6 +409,16 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		++s->launches;
 		CK(enqueue_halo_publish(s, Rn, local_max));
 	}
+	FinalizeArgs fin {};
+	fin.cfg = s->cfg;
+	fin.state = s->d_state;
+	fin.new_pbc = s->d_scratch + 0;
+	fin.new_nbc = s->d_scratch + 1;
+	fin.new_count = s->part[Rn].count;
+	fin.max_blocks = s->desc.max_blocks;
+	fin.n_models = (int) s->models.size();
+	for(size_t m = 0; m < s->models.size(); ++m) fin.bin_capacity[m] = s->models[m].bin_capacity;
+	fin.next_max_vel = mgsp ? global_max : nullptr;
 	{
 		RegisterArgs a {};
 		a.cfg = s->cfg;
@@ -443,6 +430,11 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		a.error = &s->d_state->error;
 		a.lo = -1;
 		a.span = 3;
+		if(!mgsp) {  // the last CTA rolls the step state (MGSP: the tagging kernels come first)
+			a.done_counter = &s->d_state->done_counter;
+			a.do_finalize = 1;
+			a.fin = fin;
+		}
 		register_blocks_kernel<<<grid_blocks(4), 128, 0, st>>>(a);
 		++s->launches;
 	}
@@ -450,19 +442,7 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		mark_phase(s, 9);
 		CK(enqueue_halo_tag(s, Rn, s->d_scratch + 0, local_max, global_max));
 		mark_phase(s, 8);
-	}
-	{
-		FinalizeArgs a {};
-		a.cfg = s->cfg;
-		a.state = s->d_state;
-		a.new_pbc = s->d_scratch + 0;
-		a.new_nbc = s->d_scratch + 1;
-		a.new_count = s->part[Rn].count;
-		a.max_blocks = s->desc.max_blocks;
-		a.n_models = (int) s->models.size();
-		for(size_t m = 0; m < s->models.size(); ++m) a.bin_capacity[m] = s->models[m].bin_capacity;
-		a.next_max_vel = mgsp ? global_max : nullptr;
-		finalize_step_kernel<<<1, 32, 0, st>>>(a);
+		finalize_step_kernel<<<1, 32, 0, st>>>(fin);
 		++s->launches;
 	}
 	return (int) cudaGetLastError();
@@ -582,12 +562,10 @@ void preload_kernels() {
 	preload(clear_grid_kernel);
 	preload(carry_grid_kernel);
 	preload(scan_kernel);
-	preload(scan_batch_kernel);
-	preload(block_summary_kernel);
+	preload(summary_kernel);
 	preload(rebuild_kernel);
 	preload(register_blocks_kernel);
 	preload(finalize_step_kernel);
-	preload(snapshot_int_kernel);
 	preload(cell_bucket_to_block_kernel);
 	preload(compute_bin_capacity_kernel);
 	preload(activate_blocks_kernel);
@@ -654,8 +632,11 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 		CK(s->desc.mgsp_world > 1 ? cudaMalloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)) : pool_alloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
 		CK(cudaMemsetAsync(s->grid[i], 0, (mb + 1) * kGridBlockFloats * sizeof(float), s->stream));
 	}
-	CK(pool_alloc(&s->marks, (mb + 2) * sizeof(int)));
-	CK(pool_alloc(&s->dest, (mb + 2) * sizeof(int)));
+	{
+		const size_t tiles = (mb + kRebuildTile - 1) / kRebuildTile + 1;
+		CK(pool_alloc(&s->tile_sums, tiles * kScanComps * sizeof(int)));
+		CK(pool_alloc(&s->block_totals, (size_t) kMaxModels * mb * sizeof(int)));
+	}
 	CK(pool_alloc(&s->d_scratch, 16 * sizeof(int)));
 	CK(cudaMemsetAsync(s->d_scratch, 0, 16 * sizeof(int), s->stream));
 	if(s->desc.mgsp_world > 1) {
@@ -711,8 +692,8 @@ int cb200_sim_destroy(cb200_sim* s) {
 		g_pool.release(m.d_out);
 		cudaFreeHost(m.h_out);
 	}
-	g_pool.release(s->marks);
-	g_pool.release(s->dest);
+	g_pool.release(s->tile_sums);
+	g_pool.release(s->block_totals);
 	g_pool.release(s->d_scratch);
 	g_pool.release(s->d_state);
 	g_pool.release(s->peer_overlap_keys);

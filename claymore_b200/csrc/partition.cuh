@@ -98,12 +98,6 @@ __device__ __forceinline__ void scan_body(const ScanArgs& a) {
 	}
 }
 __global__ void __launch_bounds__(1024) scan_kernel(const ScanArgs a) { scan_body(a); }
-// several independent scans in one launch (one CTA each): the per-model bin-offset scans of a sub-step
-struct ScanBatch {
-	ScanArgs a[kMaxModels];
-};
-__global__ void __launch_bounds__(1024) scan_batch_kernel(const ScanBatch b) { scan_body(b.a[blockIdx.x]); }
-
 // exclusive_scan_inverse (Library/MnBase/Algorithm/MappingKernels.cuh:44-55)
 __global__ void scan_inverse_kernel(int num, const int* map, int* map_inv) {
 	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num; i += gridDim.x * blockDim.x) {
@@ -158,63 +152,150 @@ __global__ void __launch_bounds__(kBucketThreads) cell_bucket_to_block_kernel(Cf
 }
 
 // ------------------------------------------------------------------------------------------------
-// step-driver fused kernels
+// step-driver fused kernels.  The reference's rebuild is: mark_active_particle_blocks, thrust::exclusive_scan of the
+// marks (gmpm_simulator.cuh:257-260), update_partition (mgmpm_kernels.cuh:966-977), cell_bucket_to_block + update_buckets,
+// compute_bin_capacity and a second thrust scan.  Here: two launches over tiles of 64 old blocks, no single-CTA scan:
+//   summary_kernel   per tile: particle totals of its blocks, the tile's aggregates (marked blocks, bins per model);
+//                    the LAST CTA to finish scans the few thousand tile aggregates and writes the totals;
+//   rebuild_kernel   per tile: scan inside the tile + the tile prefix = new block number / bin offset of every marked
+//                    block; keys, table, buckets are written straight in the new numbering.
 // ------------------------------------------------------------------------------------------------
-// (1) per old block: particle count per model, activity mark; also un-insert the keys of the partition that is
-//     about to be rebuilt (replaces cudaMemsetAsync(0xff, 4*G^3), hash_table.cuh:110-112, by touching only the
-//     entries that were set).
+constexpr int kRebuildTile = 64;        // old blocks per CTA
+constexpr int kSummaryThreads = 256;    // 8 warps x 8 blocks (eight independent row loads in flight per warp)
+constexpr int kRebuildThreads = 1024;   // 32 warps x 2 blocks: a marked block costs a dozen dependent gather rounds
+constexpr int kScanComps = kMaxModels + 1;  // component 0: marked blocks, 1 + m: bins of model m
+
 struct SummaryArgs {
 	Cfg cfg;
-	const StepState* state;
+	StepState* state;
 	int n_models;
 	const int* cell_counts[kMaxModels];  // next buffers' cell_particle_counts (old numbering)
-	int* bucket_sizes[kMaxModels];       // next buffers' particle_bucket_sizes (old numbering)
-	int* marks;                          // [ebc + 1]
-	int* stale_table;                    // table of the partition being rebuilt
+	int* block_totals;                   // [n_models][max_blocks]: particles per old block
+	int* tile_sums;                      // [tiles][kScanComps]: aggregate, then (last CTA) exclusive prefix
+	int max_blocks;
+	// the partition that is about to be rebuilt: un-insert its keys (replaces cudaMemsetAsync(0xff, 4*G^3),
+	// hash_table.cuh:110-112, by touching only the entries that were set) -- in this launch, because every stale
+	// entry must be gone before rebuild_kernel writes the first new one
+	int* stale_table;
 	const int* stale_keys;
-	const int* stale_count;              // number of keys currently inserted in stale_table
-	int capacity;
+	int* stale_count;                    // Partition::count: stale count in, number of new particle blocks out
+	int* new_pbc;
+	int* bin_offsets[kMaxModels];        // cur buffers: [new_pbc] = total bins
 };
-__global__ void __launch_bounds__(256) block_summary_kernel(const SummaryArgs a) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kSummaryThreads) summary_kernel(const SummaryArgs a) {
+	constexpr int PER_WARP = kRebuildTile / (kSummaryThreads / 32);
+	__shared__ int s_tot[kMaxModels][kRebuildTile];
+	__shared__ int s_last;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nm = a.n_models, nc = nm + 1;
 	const int ebc = a.state->ebc;
-	for(int b = blockIdx.x * 8 + warp; b <= ebc; b += gridDim.x * 8) {
-		int any = 0;
-		if(b < ebc) {
-			for(int m = 0; m < a.n_models; ++m) {
-				const int2 c = reinterpret_cast<const int2*>(a.cell_counts[m] + (size_t) b * kBlockVol)[lane];
-				const int s = __reduce_add_sync(0xffffffffu, c.x + c.y);
-				if(lane == 0) a.bucket_sizes[m][b] = s;
-				any |= s;
-			}
-		}
-		if(lane == 0) a.marks[b] = any > 0;
-	}
-	const int stale = min(*a.stale_count, a.capacity);
-	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < stale; i += gridDim.x * blockDim.x) {
+	const int n_tiles = (ebc + kRebuildTile - 1) / kRebuildTile;
+	const int stale = min(*(volatile int*) a.stale_count, a.max_blocks);
+	for(int i = blockIdx.x * blockDim.x + tid; i < stale; i += gridDim.x * blockDim.x) {
 		const int x = a.stale_keys[3 * i], y = a.stale_keys[3 * i + 1], z = a.stale_keys[3 * i + 2];
 		if(in_domain(a.cfg, x, y, z)) a.stale_table[table_offset(a.cfg, x, y, z)] = -1;
 	}
+	const int tile = blockIdx.x, b0 = tile * kRebuildTile;
+	if(tile < n_tiles) {
+		// warp w sums the cell counts of its blocks (one coalesced 256-byte row per block and model)
+#pragma unroll
+		for(int j = 0; j < PER_WARP; ++j) {
+			const int t = warp * PER_WARP + j, b = b0 + t;
+			for(int m = 0; m < nm; ++m) {
+				int tot = 0;
+				if(b < ebc) {
+					const int2 c = reinterpret_cast<const int2*>(a.cell_counts[m] + (size_t) b * kBlockVol)[lane];
+					tot = __reduce_add_sync(0xffffffffu, c.x + c.y);
+				}
+				if(lane == 0) {
+					s_tot[m][t] = tot;
+					if(b < ebc) a.block_totals[(size_t) m * a.max_blocks + b] = tot;
+				}
+			}
+		}
+		__syncthreads();
+		if(warp == 0) {
+			for(int c = 0; c < nc; ++c) {
+				int v = 0;
+#pragma unroll
+				for(int h = 0; h < kRebuildTile / 32; ++h) {
+					const int t = h * 32 + lane;
+					if(c == 0) {
+						int any = 0;
+						for(int m = 0; m < nm; ++m) any |= s_tot[m][t];
+						v += any > 0;
+					} else {
+						v += (s_tot[c - 1][t] + kBinCap - 1) / kBinCap;
+					}
+				}
+				v = __reduce_add_sync(0xffffffffu, v);
+				if(lane == 0) a.tile_sums[(size_t) tile * kScanComps + c] = v;
+			}
+		}
+	}
+	// ---- the last CTA to finish turns the tile aggregates into exclusive prefixes and publishes the totals
+	__syncthreads();
+	if(tid == 0) {
+		__threadfence();
+		s_last = atomicAdd(&a.state->done_counter, 1) == (int) gridDim.x - 1;
+	}
+	__syncthreads();
+	if(!s_last) return;
+	__threadfence();
+	if(tid == 0) a.state->done_counter = 0;
+	// CTA-wide scan per component: thread i owns the tiles [i K, (i + 1) K)
+	{
+		__shared__ int s_wsum[kSummaryThreads / 32];
+		const int K = (n_tiles + kSummaryThreads - 1) / kSummaryThreads;
+		for(int c = 0; c < nc; ++c) {
+			volatile int* col = a.tile_sums + c;
+			int sum = 0;
+			for(int k = 0; k < K; ++k) {
+				const int t = tid * K + k;
+				if(t < n_tiles) sum += col[(size_t) t * kScanComps];
+			}
+			int inc = sum;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				const int u = __shfl_up_sync(0xffffffffu, inc, o);
+				if(lane >= o) inc += u;
+			}
+			if(lane == 31) s_wsum[warp] = inc;
+			__syncthreads();
+			int base = 0, total = 0;
+#pragma unroll
+			for(int w = 0; w < kSummaryThreads / 32; ++w) {
+				const int v = s_wsum[w];
+				if(w < warp) base += v;
+				total += v;
+			}
+			int run = base + inc - sum;  // exclusive prefix of this thread's first tile
+			for(int k = 0; k < K; ++k) {
+				const int t = tid * K + k;
+				if(t < n_tiles) {
+					const int v = col[(size_t) t * kScanComps];
+					col[(size_t) t * kScanComps] = run;
+					run += v;
+				}
+			}
+			if(tid == 0) col[(size_t) n_tiles * kScanComps] = total;  // grand total behind the last tile
+			__syncthreads();
+		}
+	}
+	__syncthreads();
+	if(tid == 0) {
+		volatile int* tot = a.tile_sums + (size_t) n_tiles * kScanComps;
+		const int n_new = tot[0];
+		*a.new_pbc = n_new;
+		*a.stale_count = n_new;
+		if(n_new > a.max_blocks) atomicOr(&a.state->error, kErrBlockCapacity);
+		for(int m = 0; m < nm; ++m) {
+			a.bin_offsets[m][n_new] = tot[1 + m];
+			a.state->bin_count[m] = tot[1 + m];
+		}
+	}
 }
 
-// (2) compaction: old block b with a mark becomes block dest[b] of the new partition (update_partition,
-//     mgmpm_kernels.cuh:966-977); its cell buckets are flattened straight into the other buffer's block bucket in
-//     the new numbering (cell_bucket_to_block + update_buckets) and its bin demand is recorded (compute_bin_capacity).
-struct RebuildArgs {
-	Cfg cfg;
-	const StepState* state;
-	int n_models;
-	const int* marks;
-	const int* dest;
-	const int* old_keys;
-	int* new_keys;
-	int* new_table;
-	const int* cell_counts[kMaxModels];  // next buffers (old numbering)
-	const int* cellbuckets[kMaxModels];
-	int* dst_sizes[kMaxModels];          // cur buffers (new numbering)
-	int* dst_buckets[kMaxModels];
-	int* bin_sizes[kMaxModels];
-};
 // one WARP per old block: the 64 cell counts are prefix-summed with shuffles, a tag finds its cell by a 6-step binary
 // search over the lane-distributed prefix (shuffles, no shared memory, no block barrier), so the eight warps of a CTA
 // stream independent blocks and hide each other's latency.
@@ -231,6 +312,7 @@ __device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __r
 	const int p_even = inc - pair;       // exclusive prefix of cell 2*lane
 	const int p_odd = p_even + c.x;      // exclusive prefix of cell 2*lane + 1
 	const int total = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll 2
 	for(int i0 = 0; i0 < total; i0 += 32) {
 		const int i = i0 + lane;
 		// largest lane L with p_even(L) <= i
@@ -249,13 +331,65 @@ __device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __r
 	}
 	return total;
 }
-__global__ void __launch_bounds__(256) rebuild_kernel(const RebuildArgs a) {
+
+struct RebuildArgs {
+	Cfg cfg;
+	const StepState* state;
+	int n_models;
+	const int* old_keys;
+	int* new_keys;
+	int* new_table;
+	const int* block_totals;             // from summary_kernel
+	const int* tile_sums;                // exclusive tile prefixes
+	int max_blocks;
+	const int* cell_counts[kMaxModels];  // next buffers (old numbering)
+	const int* cellbuckets[kMaxModels];
+	int* dst_sizes[kMaxModels];          // cur buffers (new numbering)
+	int* dst_buckets[kMaxModels];
+	int* bin_offsets[kMaxModels];        // cur buffers: exclusive scan of the bin demand
+};
+__global__ void __launch_bounds__(kRebuildThreads) rebuild_kernel(const RebuildArgs a) {
+	constexpr int PER_WARP = kRebuildTile / (kRebuildThreads / 32);
+	static_assert(kRebuildTile == 64, "the tile scan below is written for two warps");
+	__shared__ int s_tot[kMaxModels][kRebuildTile];
+	__shared__ int s_pre[kScanComps][kRebuildTile];  // exclusive prefix inside a 32-block half
+	__shared__ int s_half[kScanComps];               // aggregate of the first half
 	const Cfg& cfg = a.cfg;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nm = a.n_models, nc = nm + 1;
 	const int ebc = a.state->ebc;
-	for(int b = blockIdx.x * 8 + warp; b < ebc; b += gridDim.x * 8) {
-		if(!a.marks[b]) continue;
-		const int nb = a.dest[b];
+	const int tile = blockIdx.x, b0 = tile * kRebuildTile;
+	if(b0 >= ebc) return;
+	if(tid < kRebuildTile) {  // thread t = block b0 + t
+		const int b = b0 + tid;
+		int any = 0;
+		for(int m = 0; m < nm; ++m) {
+			const int tot = b < ebc ? a.block_totals[(size_t) m * a.max_blocks + b] : 0;
+			s_tot[m][tid] = tot;
+			any |= tot;
+		}
+		for(int c = 0; c < nc; ++c) {
+			const int v = c == 0 ? (any > 0) : (s_tot[c - 1][tid] + kBinCap - 1) / kBinCap;
+			int inc = v;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				const int u = __shfl_up_sync(0xffffffffu, inc, o);
+				if(lane >= o) inc += u;
+			}
+			s_pre[c][tid] = inc - v;
+			if(tid == 31) s_half[c] = inc;
+		}
+	}
+	__syncthreads();
+	// ---- compaction: warp per marked old block
+	for(int j = 0; j < PER_WARP; ++j) {
+		const int t = warp * PER_WARP + j, b = b0 + t;
+		if(b >= ebc) break;
+		int any = 0;
+		for(int m = 0; m < nm; ++m) any |= s_tot[m][t];
+		if(!any) continue;
+		const int* tp = a.tile_sums + (size_t) tile * kScanComps;
+		const int nb = tp[0] + s_pre[0][t] + (t >= 32 ? s_half[0] : 0);
 		if(lane == 0) {
 			const int x = a.old_keys[3 * b], y = a.old_keys[3 * b + 1], z = a.old_keys[3 * b + 2];
 			a.new_keys[3 * nb] = x;
@@ -263,40 +397,24 @@ __global__ void __launch_bounds__(256) rebuild_kernel(const RebuildArgs a) {
 			a.new_keys[3 * nb + 2] = z;
 			a.new_table[table_offset(cfg, x, y, z)] = nb;
 		}
-		for(int m = 0; m < a.n_models; ++m) {
+		for(int m = 0; m < nm; ++m) {
+			if(s_tot[m][t] == 0) {  // nothing to flatten
+				if(lane == 0) {
+					a.dst_sizes[m][nb] = 0;
+					a.bin_offsets[m][nb] = tp[1 + m] + s_pre[1 + m][t] + (t >= 32 ? s_half[1 + m] : 0);
+				}
+				continue;
+			}
 			const int total = warp_flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift));
 			if(lane == 0) {
 				a.dst_sizes[m][nb] = total;
-				a.bin_sizes[m][nb] = (total + kBinCap - 1) / kBinCap;
+				a.bin_offsets[m][nb] = tp[1 + m] + s_pre[1 + m][t] + (t >= 32 ? s_half[1 + m] : 0);
 			}
 		}
 	}
 }
 
-// (3) neighbour / exterior registration (register_neighbor_blocks :117-133, register_exterior_blocks :135-151):
-//     one thread per (particle block, offset) so the CAS traffic is spread over the whole grid.
-struct RegisterArgs {
-	Cfg cfg;
-	Count block_count;  // particle blocks of the partition
-	int* table;
-	int* keys;
-	int* count;
-	int capacity;
-	int* error;
-	int lo, span;       // offsets per axis in [lo, lo+span): (0,2) neighbours, (-1,3) exterior
-};
-__global__ void register_blocks_kernel(const RegisterArgs a) {
-	const int n = a.block_count.get();
-	const int per = a.span * a.span * a.span;
-	const long long total = (long long) n * per;
-	for(long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-		const int b = (int) (t / per), o = (int) (t % per);
-		const int i = o / (a.span * a.span) + a.lo, j = (o / a.span) % a.span + a.lo, k = o % a.span + a.lo;
-		partition_insert(a.cfg, a.table, a.keys, a.count, a.capacity, a.error, a.keys[3 * b] + i, a.keys[3 * b + 1] + j, a.keys[3 * b + 2] + k);
-	}
-}
-
-// (4) end of sub-step: roll the device-resident counters and clock (gmpm_simulator.cuh:578-579 and the
+// (3) end of sub-step: roll the device-resident counters and clock (gmpm_simulator.cuh:578-579 and the
 //     D2H counter copies at :462,:502,:517,:564)
 struct FinalizeArgs {
 	Cfg cfg;
@@ -309,8 +427,7 @@ struct FinalizeArgs {
 	long long bin_capacity[kMaxModels];
 	const float* next_max_vel;  // nullable (MGSP): global max |v|^2 of the grid the next sub-step starts from
 };
-__global__ void finalize_step_kernel(const FinalizeArgs a) {
-	if(threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void finalize_step(const FinalizeArgs& a) {
 	StepState* s = a.state;
 	const float next_dt = [&] {
 		float dt = s->dt_default;
@@ -324,7 +441,7 @@ __global__ void finalize_step_kernel(const FinalizeArgs a) {
 	s->prev_ebc = s->ebc;
 	s->pbc = *a.new_pbc;
 	s->nbc = *a.new_nbc;
-	s->ebc = min(*a.new_count, a.max_blocks);
+	s->ebc = min(*(volatile const int*) a.new_count, a.max_blocks);
 	for(int m = 0; m < a.n_models; ++m)
 		if(s->bin_count[m] > a.bin_capacity[m]) s->error |= kErrBinCapacity;
 	s->dt = next_dt;
@@ -334,10 +451,50 @@ __global__ void finalize_step_kernel(const FinalizeArgs a) {
 	s->work_counter2 = 0;
 	s->steps += 1;
 }
-
-__global__ void snapshot_int_kernel(const int* src, int* dst) {
-	if(threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+__global__ void finalize_step_kernel(const FinalizeArgs a) {
+	if(threadIdx.x == 0 && blockIdx.x == 0) finalize_step(a);
 }
+
+// (4) neighbour / exterior registration (register_neighbor_blocks :117-133, register_exterior_blocks :135-151):
+//     one thread per (particle block, offset) so the CAS traffic is spread over the whole grid.
+struct RegisterArgs {
+	Cfg cfg;
+	Count block_count;  // particle blocks of the partition
+	int* table;
+	int* keys;
+	int* count;
+	int capacity;
+	int* error;
+	int lo, span;       // offsets per axis in [lo, lo+span): (0,2) neighbours, (-1,3) exterior
+	// what the LAST CTA to finish does, in place of one-thread kernels of their own:
+	int* done_counter;  // nullable: zero before the launch, zero again after it
+	int* snapshot_out;  // nullable: receives *count once every insertion of this launch is done
+	int do_finalize;    // roll the step state (fin)
+	FinalizeArgs fin;
+};
+__global__ void register_blocks_kernel(const RegisterArgs a) {
+	const int n = a.block_count.get();
+	const int per = a.span * a.span * a.span;
+	const long long total = (long long) n * per;
+	for(long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+		const int b = (int) (t / per), o = (int) (t % per);
+		const int i = o / (a.span * a.span) + a.lo, j = (o / a.span) % a.span + a.lo, k = o % a.span + a.lo;
+		partition_insert(a.cfg, a.table, a.keys, a.count, a.capacity, a.error, a.keys[3 * b] + i, a.keys[3 * b + 1] + j, a.keys[3 * b + 2] + k);
+	}
+	if(a.done_counter) {
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			__threadfence();
+			if(atomicAdd(a.done_counter, 1) == (int) gridDim.x - 1) {
+				__threadfence();
+				*a.done_counter = 0;
+				if(a.snapshot_out) *a.snapshot_out = *(volatile int*) a.count;
+				if(a.do_finalize) finalize_step(a.fin);
+			}
+		}
+	}
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // drop-in forms of the remaining reference kernels (one thread per element)
