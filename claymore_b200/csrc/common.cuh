@@ -163,16 +163,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm v
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+	// the suspend-time hint parks the thread instead of letting 192 of them spin through the issue slots
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
 		"WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 		"@p bra DONE_%=;\n"
 		"bra WAIT_%=;\n"
 		"DONE_%=:\n"
 		"}\n" ::"r"(smem_u32(bar)),
-		"r"(parity)
+		"r"(parity), "r"(0x989680u)
 		: "memory");
 }
 // global -> shared 1-D bulk copy, completion on an mbarrier (SASS: UBLKCP)

@@ -40,6 +40,9 @@ namespace cb200 {
 #ifndef CB200_G2P2G_ASYNC
 #define CB200_G2P2G_ASYNC 1     // particle gathers by cp.async into the particle's own (not yet written) record slot
 #endif
+#ifndef CB200_G2P2G_EARLYPOS
+#define CB200_G2P2G_EARLYPOS 1  // first particle's position copies are issued before the wait for the neighbourhood (one more barrier)
+#endif
 #ifndef CB200_G2P2G_ROUNDS2
 #define CB200_G2P2G_ROUNDS2 1   // registers -> arena in 2 rounds (half-warp pairs of one node plane combined by shuffles) instead of 3
 #endif
@@ -86,7 +89,7 @@ __device__ __forceinline__ int acc_off_z(int Z) { return (Z >> 2) * 256 + (Z & 3
 struct G2P2GSmem {
 	float4 vel4[512];                // node-major velocity arena, index (X*8+Y)*8+Z
 	float acc[8 * 256];              // accumulation arena (grid-block layout)
-	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads; its first 6 KiB double as the TMA landing
+	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads; 6 KiB of quad 1 double as the TMA landing
 	                                 // zone (8 blocks x 3 channels x 64 cells) while a block's neighbourhood is staged
 	unsigned short idx[kChunk];      // staged slots sorted by cell
 	unsigned short movers[kChunk];   // staged slots of particles that changed cell
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	G2P2GSmem& sm = *reinterpret_cast<G2P2GSmem*>(smem_raw);
 	uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar);
-	float* const velsoa = reinterpret_cast<float*>(&sm.rec[0][0]);  // consumed (transposed into vel4) before any record is staged
+	float* const velsoa = reinterpret_cast<float*>(&sm.rec[1][0]);  // landing zone of the TMA copies: consumed (transposed into vel4)
+	                                                                // before anything is staged in quads 1-3 of the records
 
 	const Cfg& cfg = a.cfg;
 	const int tid = threadIdx.x;
@@ -214,6 +218,34 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		}
 		bool acc_dirty = true;  // the arena still feeds the previous block's bulk reductions: it is drained and zeroed just
 		                        // before this block's first accumulation, i.e. behind its whole phase 1
+#if CB200_G2P2G_ASYNC
+		// source row of the particle staged in `slot` (its gather tag sits in vel4[slot].w) and the copy of its position
+		auto src_of = [&](const float* bins, int slot) {
+			const int tag = __float_as_int(sm.vel4[slot].w);
+			const int sp = tag & ppb_mask;
+			return bins + ((size_t) sm.srcbin[tag >> cfg.ppb_shift] + (sp >> 5)) * BINF + (sp & 31);
+		};
+		auto fetch_pos = [&](const float* bins, int slot) {
+			const float* sb = src_of(bins, slot);
+			float* dst = &sm.rec[0][rec_slot(slot)].x;
+			cp_async4(dst, sb);
+			cp_async4(dst + 1, sb + 32);
+			cp_async4(dst + 2, sb + 64);
+		};
+		bool primed = false;  // tags and first positions of (model 0, chunk 0) already requested
+#if CB200_G2P2G_EARLYPOS
+		{
+			const int size0 = min(a.m[0].next.particle_bucket_sizes[blk], kChunk);
+			__syncthreads();  // S1: srcbin
+			if(size0 > 0) {
+				cp_async_wait<0>();  // this thread's tags
+				if(tid < size0) fetch_pos(a.m[0].cur.bins, tid);
+				cp_async_commit();
+				primed = true;
+			}
+		}
+#endif
+#endif
 		mbar_wait(bar, phase);
 		phase ^= 1;
 		// SoA landing zone -> one float4 per node (zero where the grid block does not exist)
@@ -264,27 +296,17 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			// memory): tags sit in vel4[].w; the position of particle `slot` is copied into rec[0][slot] and its F / J / logJp into
 			// rec[1..3][slot] -- the particle's own record slot, which is written only at the end of its iteration.  Positions
 			// run one iteration ahead, F is in flight during G2P.
-			if(!(mi == 0 && c0 == 0)) {
+			if(!(primed && mi == 0 && c0 == 0)) {
+				if(!(mi == 0 && c0 == 0)) {  // (model 0, chunk 0): tags were requested at the top of the block
 #pragma unroll
-				for(int it = 0; it < ITERS; ++it)
-					if(it * T + tid < nchunk) cp_async4(&sm.vel4[it * T + tid].w, bucket + c0 + it * T + tid);
+					for(int it = 0; it < ITERS; ++it)
+						if(it * T + tid < nchunk) cp_async4(&sm.vel4[it * T + tid].w, bucket + c0 + it * T + tid);
+					cp_async_commit();
+				}
+				cp_async_wait<0>();
+				if(tid < nchunk) fetch_pos(M.cur.bins, tid);
 				cp_async_commit();
 			}
-			cp_async_wait<0>();
-			auto src_of = [&](int slot) {
-				const int tag = __float_as_int(sm.vel4[slot].w);
-				const int sp = tag & ppb_mask;
-				return M.cur.bins + ((size_t) sm.srcbin[tag >> cfg.ppb_shift] + (sp >> 5)) * BINF + (sp & 31);
-			};
-			auto fetch_pos = [&](int slot) {
-				const float* sb = src_of(slot);
-				float* dst = &sm.rec[0][rec_slot(slot)].x;
-				cp_async4(dst, sb);
-				cp_async4(dst + 1, sb + 32);
-				cp_async4(dst + 2, sb + 64);
-			};
-			if(tid < nchunk) fetch_pos(tid);
-			cp_async_commit();
 #endif
 			int cr0 = -1, cr1 = -1, cr2 = -1;  // (home cell << 16) | rank of the up-to-three particles of this thread
 			static_assert(ITERS <= 3, "cellrank registers");
@@ -297,7 +319,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int pidib = c0 + slot;
 #if CB200_G2P2G_ASYNC
 				const int rs = rec_slot(slot);
-				const float* __restrict__ sbin = src_of(slot);
+				const float* __restrict__ sbin = src_of(M.cur.bins, slot);
 				{  // group A: the channels needed after G2P
 					float* dst = &sm.rec[1][rs].x;
 					if constexpr(MAT == CB200_J_FLUID) {
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					pos[1] = p4.y;
 					pos[2] = p4.z;
 				}
-				if(slot + T < nchunk) fetch_pos(slot + T);  // group B: next particle's position, a whole iteration ahead
+				if(slot + T < nchunk) fetch_pos(M.cur.bins, slot + T);  // group B: next particle's position, a whole iteration ahead
 				cp_async_commit();
 #else
 				const int advect = __ldg(bucket + pidib);
