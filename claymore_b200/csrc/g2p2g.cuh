@@ -4,28 +4,33 @@
 // fetch_particle_buffer_data :428-462, calculate_contribution_and_store_particle_data :470-663 and
 // ParticleBufferImpl::add_advection particle_buffer.cuh:100-135).  Same inputs, same outputs, same containers;
 // different machine mapping:
-//   * one CTA of 192 threads walks particle blocks (persistent, grid-stride) instead of one 128-thread CUDA block
-//     per particle block;
+//   * one CTA of 192 threads pulls particle blocks from a device-side queue (persistent grid, 4 CTAs per SM) instead
+//     of one 128-thread CUDA block per particle block;
 //   * the 2x2x2 neighbourhood of grid blocks is staged with eight 768-byte TMA bulk copies (the three velocity
 //     channels of a grid block are contiguous) signalled on an mbarrier, then transposed in shared memory to one
 //     float4 per node so that G2P issues 27 LDS.128 instead of 81 LDS.32 (reference: 1536 scalar global loads each
 //     preceded by a table query, :700-726);
+//   * the particle gathers are a software pipeline of 4-byte cp.async copies (no registers held, no reliance on the
+//     ~20 KB of L1 left beside 208 KB of shared memory): tags land in the unused w words of the velocity arena, a
+//     particle's position / F / J / logJp in its own staged-record slot, which is written only at the end of its
+//     iteration; positions run one particle ahead, F is in flight during G2P;
 //   * P2G does NOT scatter per particle.  Shared-memory float atomicAdd is a compare-and-swap loop on this
 //     hardware (LDS, FADD, ATOMS.CAST.SPIN, BRA) and 108 of them per particle were 63 % of all instructions in the
 //     first version of this kernel (profiles/r01_v0_*).  Instead:
 //       phase 1  particle-parallel: gather, G2P, advection, F update, stress, bin store, re-bucketing; the P2G
 //                inputs of each particle (local position, q = m v - C x_p, D = C dx: 15 floats) are staged in
-//                shared memory and counting-sorted by cell with native integer shared atomics;
-//       phase 2  cell-parallel: thread (cell, i-slice) walks the particles of its cell and accumulates its 9 nodes x
-//                4 channels in registers, then adds them to the arena once per cell: 108 adds per CELL, not per
-//                particle, and never two lanes of one instruction on the same address;
-//       phase 3  the few particles that changed cell in this step are scattered node-parallel.
+//                shared memory (XOR-swizzled slots) and counting-sorted by cell with native integer shared atomics;
+//       phase 2  cell-parallel: thread (cell, x-slice) walks the particles of its cell and accumulates its 9 nodes x
+//                4 channels in registers: 108 adds per CELL, not per particle; registers -> arena by plain
+//                read-add-write in two rounds of plane-disjoint (half-)warps, no atomics;
+//       phase 3  the few particles that changed cell in this step are scattered node-parallel (atomics);
 //   * the arena has the grid-block layout, so the write-back is eight 1-KiB cp.reduce.async.bulk f32-add operations
-//     executed by the TMA unit, not 2048 SM-issued global atomics (:910-936);
+//     executed by the TMA unit, not 2048 SM-issued global atomics (:910-936); in MGSP mode a second bulk reduction
+//     per shared grid block goes straight into the peer GPU's grid over NVLink;
 //   * the 27 neighbour block numbers and source bin offsets are resolved once per block into shared memory instead
 //     of two dependent global loads per particle (:761-767, particle_buffer.cuh:101-102).
 // The kernel makes no assumption on the order of a block bucket (the reference's order is atomics-dependent);
-// cell-major buckets (partition.cuh) merely make the gathers of phase 1 nearly contiguous.
+// cell-major buckets (partition.cuh) merely make the gathers of phase 1 nearly contiguous and the records bank-regular.
 #pragma once
 #include "math3.cuh"
 
@@ -36,16 +41,7 @@ namespace cb200 {
 #endif
 #ifndef CB200_G2P2G_MIN_CTAS
 #define CB200_G2P2G_MIN_CTAS 4  // measured on B200 (5M / 40M spheres): 2 CTAs/SM 6.4 / 7.0, 3: 7.7 / 8.5, 4: 8.4 / 9.3 G particle-steps/s;
-#endif                          // the kernel is latency bound (issue slots ~45 % busy), warps in flight beat spill-free registers
-#ifndef CB200_G2P2G_ASYNC
-#define CB200_G2P2G_ASYNC 1     // particle gathers by cp.async into the particle's own (not yet written) record slot
-#endif
-#ifndef CB200_G2P2G_EARLYPOS
-#define CB200_G2P2G_EARLYPOS 1  // first particle's position copies are issued before the wait for the neighbourhood (one more barrier)
-#endif
-#ifndef CB200_G2P2G_ROUNDS2
-#define CB200_G2P2G_ROUNDS2 1   // registers -> arena in 2 rounds (half-warp pairs of one node plane combined by shuffles) instead of 3
-#endif
+#endif                          // (first kernel structure) the kernel is latency bound, warps in flight beat spill-free registers
 constexpr int kG2P2GThreads = CB200_G2P2G_THREADS;  // >= 192 = 64 cells x 3 stencil slices in phase 2
 static_assert(kG2P2GThreads >= 192 && kG2P2GThreads % 32 == 0, "phase 2 maps one thread to (cell, slice)");
 constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 ppc)
@@ -183,7 +179,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			continue;
 		}
 		const int kx = a.keys[3 * blk], ky = a.keys[3 * blk + 1], kz = a.keys[3 * blk + 2];
-#if CB200_G2P2G_ASYNC
 		// Gather tags of the first chunk: copied asynchronously into the unused w components of the velocity arena (512 words
 		// for 512 staged particles) while the neighbourhood is staged.  Thread t fetches the tags it will consume itself.
 		{
@@ -194,7 +189,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				if(it * T + tid < size0) cp_async4(&sm.vel4[it * T + tid].w, bucket0 + it * T + tid);
 			cp_async_commit();
 		}
-#endif
 
 		// ---- stage the neighbourhood -------------------------------------------------------------
 		// (the landing zone aliases the records of the previous block: its last readers are behind that block's B6)
@@ -218,7 +212,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		}
 		bool acc_dirty = true;  // the arena still feeds the previous block's bulk reductions: it is drained and zeroed just
 		                        // before this block's first accumulation, i.e. behind its whole phase 1
-#if CB200_G2P2G_ASYNC
 		// source row of the particle staged in `slot` (its gather tag sits in vel4[slot].w) and the copy of its position
 		auto src_of = [&](const float* bins, int slot) {
 			const int tag = __float_as_int(sm.vel4[slot].w);
@@ -233,7 +226,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			cp_async4(dst + 2, sb + 64);
 		};
 		bool primed = false;  // tags and first positions of (model 0, chunk 0) already requested
-#if CB200_G2P2G_EARLYPOS
 		{
 			const int size0 = min(a.m[0].next.particle_bucket_sizes[blk], kChunk);
 			__syncthreads();  // S1: srcbin
@@ -244,8 +236,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				primed = true;
 			}
 		}
-#endif
-#endif
 		mbar_wait(bar, phase);
 		phase ^= 1;
 		// SoA landing zone -> one float4 per node (zero where the grid block does not exist)
@@ -255,13 +245,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int X = n >> 6, Y = (n >> 3) & 7, Z = n & 7;
 				const int bi = ((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2);
 				const int o = bi * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
-#if CB200_G2P2G_ASYNC
 				const bool ok = (valid >> bi) & 1u;  // w holds a gather tag in flight: write x, y, z only
 				*reinterpret_cast<float2*>(&sm.vel4[n].x) = ok ? make_float2(velsoa[o], velsoa[o + 64]) : make_float2(0.f, 0.f);
 				sm.vel4[n].z = ok ? velsoa[o + 128] : 0.f;
-#else
-				sm.vel4[n] = ((valid >> bi) & 1u) ? make_float4(velsoa[o], velsoa[o + 64], velsoa[o + 128], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
 			}
 		}
 		__syncthreads();  // S2: vel4, nbr, prevno, srcbin
@@ -291,7 +277,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				}
 				first_chunk = false;
 			}
-#if CB200_G2P2G_ASYNC
 			// Software pipeline of the gathers (no registers held, no reliance on the few KB of L1 left beside 208 KB of shared
 			// memory): tags sit in vel4[].w; the position of particle `slot` is copied into rec[0][slot] and its F / J / logJp into
 			// rec[1..3][slot] -- the particle's own record slot, which is written only at the end of its iteration.  Positions
@@ -307,7 +292,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				if(tid < nchunk) fetch_pos(M.cur.bins, tid);
 				cp_async_commit();
 			}
-#endif
 			int cr0 = -1, cr1 = -1, cr2 = -1;  // (home cell << 16) | rank of the up-to-three particles of this thread
 			static_assert(ITERS <= 3, "cellrank registers");
 
@@ -317,7 +301,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int slot = it * T + tid;
 				if(slot >= nchunk) continue;
 				const int pidib = c0 + slot;
-#if CB200_G2P2G_ASYNC
 				const int rs = rec_slot(slot);
 				const float* __restrict__ sbin = src_of(M.cur.bins, slot);
 				{  // group A: the channels needed after G2P
@@ -346,26 +329,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				}
 				if(slot + T < nchunk) fetch_pos(M.cur.bins, slot + T);  // group B: next particle's position, a whole iteration ahead
 				cp_async_commit();
-#else
-				const int advect = __ldg(bucket + pidib);
-				const int dir = advect >> cfg.ppb_shift;
-				const int src_pidib = advect & ppb_mask;
-				const int sbin0 = sm.srcbin[dir];
-				const float* __restrict__ sbin = M.cur.bins + ((size_t) sbin0 + (src_pidib >> 5)) * BINF + (src_pidib & 31);
-
-				float pos[3] = {__ldg(sbin), __ldg(sbin + 32), __ldg(sbin + 64)};
-				{
-					// the remaining channels are needed only after G2P: pull their lines into L1 now (no registers held)
-					if constexpr(MAT == CB200_J_FLUID) {
-						prefetch_l1(sbin + 96);
-					} else {
-#pragma unroll
-						for(int d = 0; d < 9; ++d) prefetch_l1(sbin + (3 + d) * 32);
-						if constexpr(MAT != CB200_FIXED_COROTATED) prefetch_l1(sbin + 12 * 32);
-					}
-					if(slot + T < nchunk) prefetch_l1(bucket + pidib + T);
-				}
-#endif
 				int base[3], ab[3];
 				float lp[3], w[3][3];
 #pragma unroll
@@ -458,12 +421,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				float contrib[9];
 				float* __restrict__ dbin = M.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
 				if constexpr(MAT == CB200_J_FLUID) {
-#if CB200_G2P2G_ASYNC
 					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
 					float J = sm.rec[1][rs].x;
-#else
-					float J = __ldg(sbin + 96);
-#endif
 					J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
 					if(J < 0.1f) J = 0.1f;
 					const float voln = J * M.mat.volume;
@@ -484,14 +443,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					dbin[96] = J;
 				} else {
 					float Fo[9], F[9], G[9];
-#if CB200_G2P2G_ASYNC
 					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
 					const float4 fa = sm.rec[1][rs], fb = sm.rec[2][rs], fc = sm.rec[3][rs];
 					Fo[0] = fa.x, Fo[1] = fa.y, Fo[2] = fa.z, Fo[3] = fa.w, Fo[4] = fb.x, Fo[5] = fb.y, Fo[6] = fb.z, Fo[7] = fb.w, Fo[8] = fc.x;
-#else
-#pragma unroll
-					for(int d = 0; d < 9; ++d) Fo[d] = __ldg(sbin + (3 + d) * 32);
-#endif
 					const float sc = dt * d_inv;
 #pragma unroll
 					for(int d = 0; d < 9; ++d) G[d] = A[d] * sc + ((d & 3) ? 0.f : 1.f);
@@ -507,11 +461,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
 						stress_fixed_corotated_polar(M.mat, F, contrib);
 					} else {
-#if CB200_G2P2G_ASYNC
 						float log_jp = fc.y;
-#else
-						float log_jp = __ldg(sbin + 12 * 32);
-#endif
 						if constexpr(MAT == CB200_SAND) stress_sand(M.mat, F, contrib, log_jp);
 						else stress_nacc(M.mat, F, contrib, log_jp);
 #pragma unroll
@@ -555,9 +505,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
 				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
 				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
-#if !CB200_G2P2G_ASYNC
-				const int rs = rec_slot(slot);
-#endif
 				sm.rec[0][rs] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
 				sm.rec[1][rs] = make_float4(q0, q1, q2, contrib[0] * dx);
 				sm.rec[2][rs] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
@@ -569,9 +516,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				else if(it == 1) cr1 = cr;
 				else cr2 = cr;
 			}
-#if CB200_G2P2G_ASYNC
 			cp_async_wait<0>();
-#endif
 			if(acc_dirty && tid < 8) tma_wait_read<0>();  // the TMA unit has read the arena of the previous block
 			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete
 			if(acc_dirty) {
@@ -605,7 +550,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			// thread = (home cell hc, x-slice sl of its 3x3x3 stencil); a half-warp holds the 16 cells of one x-plane
 			const int wrp = tid >> 5;
 			const bool p2 = tid < 192;
-#if CB200_G2P2G_ROUNDS2
 			// warp: (cx, sl) of lanes 0-15 / lanes 16-31 -> node plane X = cx + sl + 1
 			//   w0: (1,0) (0,1) -> 2 2    w1: (2,0) (1,1) -> 3 3    w2: (3,0) (2,1) -> 4 4    w3: (3,1) (2,2) -> 5 5
 			//   w4: (0,0) (3,2) -> 1 6    w5: (0,2) (1,2) -> 3 4
@@ -613,10 +557,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			const int cx = wrp < 3 ? wrp + 1 - hi : (wrp == 3 ? 3 - hi : (wrp == 4 ? 3 * hi : hi));
 			const int sl = wrp < 3 ? hi : (wrp == 3 ? 1 + hi : (wrp == 4 ? 2 * hi : 2));
 			const int hc = ((cx & 3) << 4) | (lane & 15);
-#else
-			// warp w: slice w/2 of the 32 cells with x in {2(w%2), 2(w%2)+1}
-			const int sl = wrp >> 1, hc = tid & 63;
-#endif
 			const int n = p2 ? sm.cnt[hc] : 0;
 			const int st = cell_start(hc);
 			__syncthreads();  // B2: idx complete, every warp has read the cell counts
@@ -659,7 +599,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				// warps (half-warps) that own different planes never meet; the rest is ordered by rounds.
 				const int X = (hc >> 4) + 1 + sl, Y = ((hc >> 2) & 3) + 1, Z = (hc & 3) + 1;
 				const int ox = acc_off_x(X);
-#if CB200_G2P2G_ROUNDS2
 				// round 0: w0-w3 (both halves hold the same plane: exchange by shuffle, lanes 0-15 add channels 0-1, lanes 16-31
 				// channels 2-3) and w4 (planes 1 and 6, all four channels per lane); round 1: w5 (planes 3 and 4)
 #pragma unroll 1
@@ -694,32 +633,6 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					}
 					__syncthreads();
 				}
-#else
-				// warp w touches the planes {2h+sl+1, 2h+sl+2}: three rounds of plane-disjoint warps {w0, w1, w5}, {w2, w3}, {w4}
-				const int my_round = wrp == 5 ? 0 : (wrp >> 1);  // threads >= 192 (wrp >= 6) never match
-#pragma unroll 1
-				for(int round = 0; round < 3; ++round) {
-					if(round == my_round && p2) {
-#pragma unroll
-						for(int j = 0; j < 3; ++j) {
-							const int oxy = ox + acc_off_y(Y + j);
-#pragma unroll
-							for(int k = 0; k < 3; ++k) {
-								const int o = oxy + acc_off_z(Z + k);
-								if(n > 0) {
-									const float m0 = sm.acc[o], m1 = sm.acc[o + 64], m2 = sm.acc[o + 128], m3 = sm.acc[o + 192];
-									sm.acc[o] = m0 + mass * acc[j * 3 + k][0];
-									sm.acc[o + 64] = m1 + acc[j * 3 + k][1];
-									sm.acc[o + 128] = m2 + acc[j * 3 + k][2];
-									sm.acc[o + 192] = m3 + acc[j * 3 + k][3];
-								}
-								__syncwarp();
-							}
-						}
-					}
-					__syncthreads();
-				}
-#endif
 			}
 			// ================= phase 3: particles that changed cell, node-parallel ====================
 			{
