@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 	// block queue: CTAs pull particle blocks from a device counter, so a launch that shares the SMs with another launch or
 	// starts late still balances.  The queue runs two blocks ahead: thread 0 keeps the newest ticket in a register, so the
 	// atomic's round trip hides behind a whole block, and the queue shift rides on the flush barrier of the block before.
-	// Barriers per (single-chunk) block: S2, B1, B2, two or three for the arena rounds, B6.
+	// Barriers per (single-chunk) block: S1, S2, B1, B2, two for the arena rounds, B6.
 	int q_pending = 0;
 	if(tid == 0) {
 		if(a.work_counter) {
