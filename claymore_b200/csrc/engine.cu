@@ -376,9 +376,10 @@ int enqueue_halo_publish(cb200_sim* s, int P, const float* local_max);
 int enqueue_halo_tag_reset(cb200_sim* s, int P);
 int enqueue_halo_tag(cb200_sim* s, int P, const int* particle_block_count, const float* local_max, float* global_max);
 
-// End of a sub-step.  Single GPU: snapshot the neighbour count, carry the grid, register exterior blocks, roll the state.
+// End of a sub-step.  Single GPU: carry the grid, register exterior blocks (its last CTA rolls the state); the neighbour count
+// was snapshotted by the last CTA of the neighbour registration.
 // MGSP: the same, interleaved with the end-of-step exchange so that its wait sits behind local work:
-//   snapshot, reset tags -> carry (+ this rank's max |v|^2 of the new grid) -> clear the next grid -> PUBLISH keys + max
+//   reset tags -> carry (+ this rank's max |v|^2 of the new grid) -> clear the next grid -> PUBLISH keys + max
 //   -> register exterior blocks -> WAIT for the peers' messages, tag overlaps, global max -> halo block lists -> roll the state.
 // A peer may reduce into this rank's next grid as soon as it has seen this rank's message: the clear comes before the publish.
 int enqueue_carry_and_exterior(cb200_sim* s, int R) {
