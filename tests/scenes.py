@@ -21,6 +21,16 @@ def small_cube(domain_bits=6, lo=20, hi=32, material=FIXED_COROTATED, v0=(0.3, -
     return dict(domain_bits=domain_bits, models=[dict(material=material, pos=pos, v0=v0)])
 
 
+def dense_cube(domain_bits=6, lo=20, hi=28, per_axis=3, material=FIXED_COROTATED, v0=(0.4, -0.8, 0.3)):
+    """per_axis^3 particles per cell (27 -> 1728 per 4^3 block): a particle block needs several 512-particle passes of g2p2g."""
+    dx = 1.0 / (1 << domain_bits)
+    cells = np.arange(lo, hi, dtype=np.float64)
+    sub = (np.arange(per_axis, dtype=np.float64) - (per_axis - 1) / 2) / per_axis  # offsets inside round(p / dx) == cell
+    ax = (cells[:, None] + sub[None, :]).ravel() * dx
+    pos = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    return dict(domain_bits=domain_bits, models=[dict(material=material, pos=pos, v0=v0)])
+
+
 def two_spheres(domain_bits=8, radius=0.1645, centers=((0.30, 0.5, 0.5), (0.70, 0.5, 0.5)), speed=1.0, material=FIXED_COROTATED):
     """Configs 2 / 2b: two spheres flying at each other; radius 0.1645 -> 42.1 cells at 256^3, 84.2 at 512^3."""
     dx = 1.0 / (1 << domain_bits)

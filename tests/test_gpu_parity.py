@@ -375,3 +375,17 @@ def test_advance_frame_matches_reference_frame_loop(oracle, cuda_lib):
         assert st.error == 0 and abs(st.dt - osim.dt) <= 1e-9 and abs(st.step_time - float(frame)) <= 1e-7
         _compare_state(osim, esim, 1, f"after frame {f + 1}", pos_tol=5e-6, f_tol=2e-4)
     esim.close()
+
+
+def test_engine_dense_blocks_multiple_passes(oracle, cuda_lib):
+    """27 particles per cell = 1728 per particle block: g2p2g stages such a block in four 512-particle passes that share one
+    accumulation arena (reference: one CUDA block strides over the whole bucket, `particle_id_in_block += blockDim.x`, mgmpm_kernels.cuh:746)."""
+    scene = scenes.dense_cube()
+    osim = scenes.build_oracle(oracle, scene)
+    esim = scenes.build_engine(scene)
+    _compare_state(osim, esim, 1, "dense, after setup")
+    for k in range(2):
+        osim.step(4)
+        esim.step(4)
+        _compare_state(osim, esim, 1, f"dense, after {4 * (k + 1)} steps", pos_tol=5e-6, f_tol=2e-4)
+    esim.close()
