@@ -58,7 +58,7 @@ class Partition(C.Structure):
 
 class SimDesc(C.Structure):
     _fields_ = [("cfg", Config), ("dt_default", C.c_float), ("fps", C.c_int), ("max_blocks", C.c_int), ("use_graph", C.c_int),
-                ("mgsp_rank", C.c_int), ("mgsp_world", C.c_int), ("mgsp_halo_cap", C.c_int)]
+                ("mgsp_rank", C.c_int), ("mgsp_world", C.c_int), ("mgsp_halo_cap", C.c_int), ("auto_grow", C.c_int)]
 
 
 class SimStats(C.Structure):
@@ -122,6 +122,9 @@ _SIGNATURES = {
     "cb200_sim_step": [_P, _I],
     "cb200_sim_advance_frame": [_P, C.POINTER(_I)],
     "cb200_sim_sync": [_P],
+    "cb200_sim_reserve": [_P, _I],
+    "cb200_sim_check_capacity": [_P, C.POINTER(_I)],
+    "cb200_sim_capacity": [_P, C.POINTER(_I), C.POINTER(_I)],
     "cb200_sim_stats_get": [_P, C.POINTER(SimStats)],
     "cb200_sim_retrieve": [_P, _I, _P, C.POINTER(_I)],
     "cb200_sim_retrieve_pinned": [_P, _I, C.POINTER(_P), C.POINTER(_I)],

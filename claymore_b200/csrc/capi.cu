@@ -9,15 +9,22 @@
 using namespace cb200;
 
 namespace cb200 {
-int g_num_sms = 0;
+// per-DEVICE caches: one process may drive several GPUs (MGSP worker threads, mgsp_benchmark.cuh:322-323)
+constexpr int kMaxDevices = 64;
+static int g_num_sms[kMaxDevices] = {};
+static inline int current_device() {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 int num_sms() {
-	if(!g_num_sms) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-		if(g_num_sms <= 0) g_num_sms = 148;
+	const int dev = current_device();
+	if(!g_num_sms[dev]) {
+		int n = 0;
+		cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+		g_num_sms[dev] = n > 0 ? n : 148;
 	}
-	return g_num_sms;
+	return g_num_sms[dev];
 }
 static inline int grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
 	long long b = (work_items + per_block - 1) / per_block;
@@ -29,7 +36,8 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 
 template<int MAT>
 static int g2p2g_blocks_per_sm() {
-	static int v = 0;
+	static int cache[kMaxDevices] = {};  // the shared-memory opt-in is per device (function attributes are per context)
+	int& v = cache[current_device()];
 	if(!v) {
 		cudaFuncSetAttribute(g2p2g_kernel<MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(G2P2GSmem));
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, g2p2g_kernel<MAT>, kG2P2GThreads, sizeof(G2P2GSmem)) != cudaSuccess || v <= 0) v = 3;

@@ -176,6 +176,13 @@ struct cb200_sim {
 	size_t phase_used = 0;
 	bool capturing = false;
 	bool owns_stream = false;
+	int frame_roll = 0;  // mirror of StepState::frame_roll
+	// capacity polling (auto_grow): an asynchronous copy of the step state, looked at when it has arrived
+	StepState* h_poll = nullptr;  // pinned
+	cudaEvent_t poll_event = nullptr;
+	bool poll_pending = false;
+	int steps_since_poll = 0;
+	int grow_events = 0;
 };
 
 namespace {
@@ -552,9 +559,12 @@ void preload(K k) {
 	(void) cudaFuncGetAttributes(&a, k);
 }
 void preload_kernels() {
-	static bool done = false;
-	if(done) return;
-	done = true;
+	static bool done[64] = {};  // per device: modules are loaded per context
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if(dev < 0 || dev >= 64) dev = 0;
+	if(done[dev]) return;
+	done[dev] = true;
 	preload(g2p2g_kernel<CB200_J_FLUID>);
 	preload(g2p2g_kernel<CB200_FIXED_COROTATED>);
 	preload(g2p2g_kernel<CB200_SAND>);
@@ -606,7 +616,97 @@ int ensure_graph(cb200_sim* s, int R) {
 }
 }  // namespace
 
+namespace {
+// Grows one block-indexed device array: allocate the larger one, copy the live prefix, initialise the tail the way
+// cb200_sim_create / cb200_sim_init_model initialised it, release the old one.  One array at a time, so the peak is the
+// footprint plus the largest array.
+template<typename T>
+int grow_array(cb200_sim* s, T*& p, size_t old_elems, size_t new_elems, int fill_byte) {
+	T* q = nullptr;
+	CK(pool_alloc(&q, new_elems * sizeof(T)));
+	if(p && old_elems) CK(cudaMemcpyAsync(q, p, old_elems * sizeof(T), cudaMemcpyDeviceToDevice, s->stream));
+	if(new_elems > old_elems) CK(cudaMemsetAsync(q + old_elems, fill_byte, (new_elems - old_elems) * sizeof(T), s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	g_pool.release(p);
+	p = q;
+	return 0;
+}
+}  // namespace
+
 extern "C" {
+
+// In-place growth of the block capacity between sub-steps: what GmpmSimulator::check_capacity + the resize calls of main_loop do
+// (gmpm_simulator.cuh:283-300, 371-376, 404-411, 528-548), except that every live array keeps its contents (the reference
+// resizes the *next* buffers, whose contents are dead at that point of its loop; here the call may come at any sub-step
+// boundary).  The sub-step graphs are re-captured on the next step.
+int cb200_sim_reserve(cb200_sim* s, int new_max_blocks) {
+	if(!s || new_max_blocks <= 0) return (int) cudaErrorInvalidValue;
+	if(new_max_blocks <= s->desc.max_blocks) return 0;
+	if(s->desc.mgsp_world > 1) return (int) cudaErrorNotSupported;  // the next grid / inbox are mapped into the peers (CUDA IPC)
+	CK(cudaStreamSynchronize(s->stream));
+	const size_t ob = (size_t) s->desc.max_blocks, nb = (size_t) new_max_blocks;
+	for(int i = 0; i < 2; ++i) {
+		if(s->graph[i]) {
+			cudaGraphExecDestroy(s->graph[i]);
+			s->graph[i] = nullptr;
+		}
+		cb200_partition& p = s->part[i];
+		CK(grow_array(s, p.active_keys, (ob + 1) * 3, (nb + 1) * 3, 0));
+		CK(grow_array(s, p.halo_marks, ob + 1, nb + 1, 0));
+		CK(grow_array(s, p.overlap_marks, ob + 1, nb + 1, 0));
+		CK(grow_array(s, s->grid[i], (ob + 1) * kGridBlockFloats, (nb + 1) * kGridBlockFloats, 0));
+	}
+	{  // scratch of the rebuild: produced and consumed inside a sub-step, nothing to keep
+		g_pool.release(s->tile_sums);
+		g_pool.release(s->block_totals);
+		s->tile_sums = nullptr;
+		s->block_totals = nullptr;
+		const size_t tiles = (nb + kRebuildTile - 1) / kRebuildTile + 1;
+		CK(pool_alloc(&s->tile_sums, tiles * kScanComps * sizeof(int)));
+		CK(pool_alloc(&s->block_totals, (size_t) kMaxModels * nb * sizeof(int)));
+	}
+	const size_t ppb = (size_t) s->cfg.ppb;
+	for(Model& m : s->models) {
+		const size_t binf = m.material == CB200_J_FLUID ? 128 : 512;
+		const long long new_bins = (long long) m.n / kBinCap + (long long) nb;
+		for(int i = 0; i < 2; ++i) {
+			cb200_particle_buffer& pb = m.pb[i];
+			CK(grow_array(s, pb.bins, (size_t) m.bin_capacity * binf, (size_t) new_bins * binf, 0));
+			CK(grow_array(s, pb.cell_particle_counts, (ob + 1) * kBlockVol, (nb + 1) * kBlockVol, 0));
+			CK(grow_array(s, pb.particle_bucket_sizes, ob + 2, nb + 2, 0));
+			CK(grow_array(s, pb.cellbuckets, (ob + 1) * ppb, (nb + 1) * ppb, 0));
+			CK(grow_array(s, pb.blockbuckets, (ob + 1) * ppb, (nb + 1) * ppb, 0));
+			CK(grow_array(s, pb.bin_offsets, ob + 2, nb + 2, 0));
+		}
+		CK(grow_array(s, m.bin_sizes, ob + 2, nb + 2, 0));
+		m.bin_capacity = new_bins;
+	}
+	s->desc.max_blocks = new_max_blocks;
+	++s->grow_events;
+	return 0;
+}
+
+// check_capacity (gmpm_simulator.cuh:283-300): when the exterior block count exceeds 3/4 of the capacity, the capacity becomes
+// 3/2 of it.  Bins need no rule of their own: their capacity is n/32 + max_blocks, an upper bound of the demand.
+// *grown (nullable) receives the new capacity, or 0 when nothing changed.  Synchronises.
+int cb200_sim_check_capacity(cb200_sim* s, int* grown) {
+	if(grown) *grown = 0;
+	if(!s || !s->setup_done) return (int) cudaErrorInvalidValue;
+	CK(pull_state(s));
+	const long long cap = s->desc.max_blocks;
+	if((long long) s->h_state->ebc * 4 > cap * 3) {
+		const long long want = cap * 3 / 2 + 1;
+		CK(cb200_sim_reserve(s, (int) want));
+		if(grown) *grown = (int) want;
+	}
+	return 0;
+}
+int cb200_sim_capacity(cb200_sim* s, int* max_blocks, int* grow_events) {
+	if(!s) return (int) cudaErrorInvalidValue;
+	if(max_blocks) *max_blocks = s->desc.max_blocks;
+	if(grow_events) *grow_events = s->grow_events;
+	return 0;
+}
 
 int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) {
 	if(!desc || !out || !cfg_valid(desc->cfg) || desc->max_blocks <= 0) return (int) cudaErrorInvalidValue;
@@ -711,6 +811,8 @@ int cb200_sim_destroy(cb200_sim* s) {
 		g_pool.release(s->interior_list[i]);
 	}
 	cudaFreeHost(s->h_state);
+	if(s->h_poll) cudaFreeHost(s->h_poll);
+	if(s->poll_event) cudaEventDestroy(s->poll_event);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return 0;
@@ -925,9 +1027,44 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	return 0;
 }
 
+static int set_frame_roll(cb200_sim* s, int on) {
+	if(s->frame_roll == on) return 0;
+	static const int kVals[2] = {0, 1};
+	s->frame_roll = on;
+	return (int) cudaMemcpyAsync(&s->d_state->frame_roll, &kVals[on], sizeof(int), cudaMemcpyHostToDevice, s->stream);
+}
+static int step_impl(cb200_sim* s, int n);
+
+// With fps > 0 the frame clock restarts on the device whenever a frame is complete (the reference's outer frame loop), so
+// stepping past a frame boundary never leaves dt at 0.
 int cb200_sim_step(cb200_sim* s, int n) {
 	if(!s || !s->setup_done) return (int) cudaErrorInvalidValue;
+	CK(set_frame_roll(s, s->desc.fps > 0 ? 1 : 0));
+	return step_impl(s, n);
+}
+// auto_grow: every 16 sub-steps an asynchronous copy of the step state is queued; once it has arrived (no host wait) the
+// reference's 3/4 rule is applied to it.  The capacity check therefore lags the simulation by at most 32 sub-steps, against
+// a head-room of 25 % of the capacity.
+static int poll_capacity(cb200_sim* s) {
+	if(s->poll_pending && cudaEventQuery(s->poll_event) == cudaSuccess) {
+		s->poll_pending = false;
+		if((long long) s->h_poll->ebc * 4 > (long long) s->desc.max_blocks * 3 && s->desc.mgsp_world <= 1) CK(cb200_sim_reserve(s, (int) ((long long) s->desc.max_blocks * 3 / 2 + 1)));
+	}
+	if(!s->poll_pending && ++s->steps_since_poll >= 16) {
+		s->steps_since_poll = 0;
+		if(!s->h_poll) {
+			CK(cudaMallocHost(&s->h_poll, sizeof(StepState)));
+			CK(cudaEventCreateWithFlags(&s->poll_event, cudaEventDisableTiming));
+		}
+		CK(cudaMemcpyAsync(s->h_poll, s->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaEventRecord(s->poll_event, s->stream));
+		s->poll_pending = true;
+	}
+	return 0;
+}
+static int step_impl(cb200_sim* s, int n) {
 	for(int i = 0; i < n; ++i) {
+		if(s->desc.auto_grow) CK(poll_capacity(s));
 		const int R = s->rollid;
 		if(s->desc.use_graph && !s->profiling) {
 			CK(ensure_graph(s, R));
@@ -948,6 +1085,7 @@ int cb200_sim_step(cb200_sim* s, int n) {
 int cb200_sim_advance_frame(cb200_sim* s, int* steps_taken) {
 	if(!s || !s->setup_done || s->desc.fps <= 0) return (int) cudaErrorInvalidValue;
 	int taken = 0;
+	CK(set_frame_roll(s, 0));  // this loop owns the frame clock
 	CK(pull_state(s));
 	// the reference restarts current_step_time at 0 for every frame
 	s->h_state->step_time = 0.f;
@@ -963,7 +1101,7 @@ int cb200_sim_advance_frame(cb200_sim* s, int* steps_taken) {
 		int batch = (int) floorf(left / s->h_state->dt_default);
 		if(batch < 1) batch = 1;
 		if(batch > 4096) batch = 4096;
-		const int e = cb200_sim_step(s, batch);
+		const int e = step_impl(s, batch);
 		if(e) return e;
 		taken += batch;
 	}

@@ -241,7 +241,7 @@ __device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const
 #pragma unroll
 	for(int i = 0; i < 9; ++i) R[i] = F[i];
 	float J = 1.f;
-	bool ok = true;
+	bool ok = false;  // set when the iteration has converged; anything else (inverted, nearly singular, slow) takes the SVD path
 #pragma unroll 1
 	for(int it = 0; it < 12; ++it) {
 		float C[9];  // cofactor matrix (column-major): R^-T = C / det
@@ -257,10 +257,7 @@ __device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const
 		const float det = R[0] * C[0] + R[3] * C[3] + R[6] * C[6];
 		if(it == 0) {
 			J = det;
-			if(det <= 1e-6f) {
-				ok = false;
-				break;
-			}
+			if(det <= 1e-6f) break;
 		}
 		const float h = __fdividef(0.5f, det);
 		float d2 = 0.f;
@@ -271,7 +268,10 @@ __device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const
 			d2 = fmaf(d, d, d2);
 			R[i] = r;
 		}
-		if(d2 < 1e-13f) break;
+		if(d2 < 1e-13f) {
+			ok = true;
+			break;
+		}
 	}
 	if(!ok) {
 		stress_fixed_corotated(m, F, PF);

@@ -439,13 +439,15 @@ __device__ __forceinline__ void finalize_step(const FinalizeArgs& a) {
 	s->next_dt = next_dt;
 	s->prev_nbc = s->nbc;
 	s->prev_ebc = s->ebc;
-	s->pbc = *a.new_pbc;
-	s->nbc = *a.new_nbc;
+	s->pbc = min(*a.new_pbc, a.max_blocks);
+	s->nbc = min(*a.new_nbc, a.max_blocks);
 	s->ebc = min(*(volatile const int*) a.new_count, a.max_blocks);
 	for(int m = 0; m < a.n_models; ++m)
 		if(s->bin_count[m] > a.bin_capacity[m]) s->error |= kErrBinCapacity;
 	s->dt = next_dt;
+	// the reference's loop increment runs after `dt = next_dt` (gmpm_simulator.cuh:324,579): the clock advances by the NEW dt
 	s->step_time += next_dt;
+	if(s->frame_roll && s->frame_time > 0.f && s->step_time >= s->frame_time) s->step_time = 0.f;
 	s->max_vel_sq = a.next_max_vel ? *a.next_max_vel : 0.f;
 	s->work_counter = 0;
 	s->work_counter2 = 0;
@@ -488,7 +490,15 @@ __global__ void register_blocks_kernel(const RegisterArgs a) {
 			if(atomicAdd(a.done_counter, 1) == (int) gridDim.x - 1) {
 				__threadfence();
 				*a.done_counter = 0;
-				if(a.snapshot_out) *a.snapshot_out = *(volatile int*) a.count;
+				// partition_insert keeps counting past the capacity (the overflow is flagged in `error`): every consumer of the
+				// count -- the snapshot, the step state, the next registration -- must see the clamped value, or the grid carry,
+				// the clears and the next grid update would index keys / grids past their max_blocks + 1 allocations
+				int c = *(volatile int*) a.count;
+				if(c > a.capacity) {
+					c = a.capacity;
+					*a.count = c;
+				}
+				if(a.snapshot_out) *a.snapshot_out = c;
 				if(a.do_finalize) finalize_step(a.fin);
 			}
 		}

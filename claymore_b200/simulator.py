@@ -18,12 +18,14 @@ class GmpmSimulator:
     DEFAULT_FRAMES = 60   # :26
 
     def __init__(self, gpu=0, dt=DEFAULT_DT, fps=DEFAULT_FPS, frames=DEFAULT_FRAMES, config=None, max_blocks=10000, use_graph=True,
-                 stream=None, mgsp_rank=0, mgsp_world=1, mgsp_halo_cap=0):
+                 stream=None, mgsp_rank=0, mgsp_world=1, mgsp_halo_cap=0, auto_grow=None):
         self.L = lib()
         self.gpu = gpu
         self.cfg = config if config is not None else Config()
         self.fps, self.nframes = fps, frames
-        self.desc = SimDesc(self.cfg, dt, fps, max_blocks, 1 if use_graph else 0, mgsp_rank, mgsp_world, mgsp_halo_cap)
+        if auto_grow is None:   # the reference checks its capacities every sub-step (gmpm_simulator.cuh:331); MGSP buffers are peer-mapped
+            auto_grow = mgsp_world <= 1
+        self.desc = SimDesc(self.cfg, dt, fps, max_blocks, 1 if use_graph else 0, mgsp_rank, mgsp_world, mgsp_halo_cap, 1 if auto_grow else 0)
         self.mgsp_rank, self.mgsp_world = mgsp_rank, mgsp_world
         self.max_blocks = max_blocks
         self._stream = C.c_void_p(stream) if stream else C.c_void_p(0)
@@ -96,6 +98,24 @@ class GmpmSimulator:
     def sync(self):
         check(self.L.cb200_sim_sync(self.h), "sync")
 
+    # ---- capacity (check_capacity + resizes, gmpm_simulator.cuh:283-300) -----------------------------
+    def reserve(self, max_blocks):
+        check(self.L.cb200_sim_reserve(self.h, int(max_blocks)), "reserve")
+        self.max_blocks = self.capacity()[0]
+
+    def check_capacity(self):
+        """Applies the reference's rule (exterior blocks > 3/4 capacity -> capacity x 3/2); returns the new capacity or 0."""
+        g = C.c_int(0)
+        check(self.L.cb200_sim_check_capacity(self.h, C.byref(g)), "check_capacity")
+        if g.value:
+            self.max_blocks = g.value
+        return g.value
+
+    def capacity(self):
+        mb, ev = C.c_int(0), C.c_int(0)
+        check(self.L.cb200_sim_capacity(self.h, C.byref(mb), C.byref(ev)), "capacity")
+        return mb.value, ev.value
+
     # ---- observation --------------------------------------------------------------------------------
     def stats(self):
         st = SimStats()
@@ -127,12 +147,14 @@ class GmpmSimulator:
         return out[: n.value]
 
     def active_keys(self):
+        self.max_blocks = self.capacity()[0]
         out = np.zeros((self.max_blocks, 3), np.int32)
         n = C.c_int(0)
         check(self.L.cb200_sim_active_keys(self.h, out.ctypes.data_as(C.c_void_p), self.max_blocks, C.byref(n)), "active_keys")
         return out[: n.value]
 
     def grid(self):
+        self.max_blocks = self.capacity()[0]
         out = np.zeros((self.max_blocks, 4, 64), np.float32)
         n = C.c_int(0)
         check(self.L.cb200_sim_grid(self.h, out.ctypes.data_as(C.c_void_p), self.max_blocks, C.byref(n)), "grid")

@@ -153,6 +153,7 @@ typedef struct cb200_sim_desc {
 	int use_graph;           /* 1: replay sub-steps from CUDA graphs */
 	int mgsp_rank, mgsp_world; /* MGSP static partition: this shard / number of shards (1 = GMPM) */
 	int mgsp_halo_cap;         /* max grid blocks shared with one peer (0 = max_blocks / 2) */
+	int auto_grow;             /* 1: cb200_sim_step applies check_capacity's rule by itself (asynchronous poll every 16 sub-steps) */
 } cb200_sim_desc;
 
 typedef struct cb200_sim_stats {
@@ -179,6 +180,13 @@ CB200_API int cb200_sim_step(cb200_sim* sim, int n);
 /* advance one frame like main_loop's inner for-loop (sub-steps until the frame time is reached) */
 CB200_API int cb200_sim_advance_frame(cb200_sim* sim, int* steps_taken);
 CB200_API int cb200_sim_sync(cb200_sim* sim);
+/* GmpmSimulator::check_capacity + the resize calls of main_loop (gmpm_simulator.cuh:283-300, 371-376, 404-411, 528-548):
+ * reserve grows every block-indexed container in place (contents kept, sub-step graphs re-captured); check_capacity applies
+ * the reference's rule (exterior blocks > 3/4 of the capacity -> capacity x 3/2) and reports the new capacity in *grown
+ * (0 = unchanged).  Both synchronise; call them between sub-steps.  Not available in MGSP mode (peer-mapped buffers). */
+CB200_API int cb200_sim_reserve(cb200_sim* sim, int new_max_blocks);
+CB200_API int cb200_sim_check_capacity(cb200_sim* sim, int* grown);
+CB200_API int cb200_sim_capacity(cb200_sim* sim, int* max_blocks, int* grow_events);
 CB200_API int cb200_sim_stats_get(cb200_sim* sim, cb200_sim_stats* out); /* synchronises */
 /* output_model  gmpm_simulator.cuh:594-634: positions to HOST float[3*n]; returns count in *n_out */
 CB200_API int cb200_sim_retrieve(cb200_sim* sim, int model, float* positions_host, int* n_out);
