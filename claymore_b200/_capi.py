@@ -137,6 +137,8 @@ _SIGNATURES = {
     "cb200_sim_mgsp_set_peers": [_P, C.POINTER(_P), C.POINTER(_P)],
     "cb200_sim_mgsp_halo_counts": [_P, C.POINTER(_I), C.POINTER(_I)],
     "cb200_trim_pool": [],
+    "cb200_test_svd3": [_I, _P, _P, _P, _P, _P],
+    "cb200_test_stress": [_I, _I, ParticleBuffer, _I, _P, _P, _P, _P, _P, _P],
     "cb200_sim_profile": [_P, _I],
     "cb200_sim_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(_I)],
     "cb200_sim_profile_phases": [_P, C.POINTER(C.c_double)],
@@ -157,6 +159,8 @@ def lib():
             fn.restype = C.c_int
         L.cb200_sim_launch_count.argtypes = [_P]
         L.cb200_sim_launch_count.restype = C.c_longlong
+        L.cb200_default_material.argtypes = [_CFG, _I, C.POINTER(ParticleBuffer)]
+        L.cb200_default_material.restype = None
         L.cb200_version.restype = C.c_char_p
         L.cb200_error_string.restype = C.c_char_p
         L.cb200_error_string.argtypes = [_I]

@@ -283,3 +283,56 @@ int cb200_reduce_grid_blocks(const cb200_config* c, int count, const int* blocki
 }
 
 }  // extern "C"
+
+// ---- test-only hooks: the device math of g2p2g on caller-supplied vectors (tests/test_gpu_scale.py) ----------------------------
+namespace cb200 {
+__global__ void test_svd_kernel(int n, const float* F, float* U, float* S, float* V) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	float f[9], u[9], s[3], v[9];
+	for(int k = 0; k < 9; ++k) f[k] = F[9 * i + k];
+	svd3(f, u, s, v);
+	for(int k = 0; k < 9; ++k) {
+		U[9 * i + k] = u[k];
+		V[9 * i + k] = v[k];
+	}
+	for(int k = 0; k < 3; ++k) S[3 * i + k] = s[k];
+}
+// mode 0: the path g2p2g takes (FIXED_COROTATED: Newton polar with SVD fall-back); mode 1: FIXED_COROTATED through the SVD
+__global__ void test_stress_kernel(int material, int mode, Mat m, int n, const float* F_in, const float* log_jp_in, float* F_out, float* PF_out, float* log_jp_out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	float f[9], pf[9];
+	for(int k = 0; k < 9; ++k) f[k] = F_in[9 * i + k];
+	float lj = log_jp_in ? log_jp_in[i] : 0.f;
+	if(material == CB200_FIXED_COROTATED) {
+		if(mode == 0) stress_fixed_corotated_polar(m, f, pf);
+		else stress_fixed_corotated(m, f, pf);
+	} else if(material == CB200_SAND) {
+		stress_sand(m, f, pf, lj);
+	} else {
+		stress_nacc(m, f, pf, lj);
+	}
+	for(int k = 0; k < 9; ++k) {
+		F_out[9 * i + k] = f[k];
+		PF_out[9 * i + k] = pf[k];
+	}
+	if(log_jp_out) log_jp_out[i] = lj;
+}
+}  // namespace cb200
+
+extern "C" {
+int cb200_test_svd3(int n, const float* F, float* U, float* S, float* V, void* stream) {
+	if(n <= 0) return 0;
+	test_svd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t) stream>>>(n, F, U, S, V);
+	return (int) cudaGetLastError();
+}
+int cb200_test_stress(int material, int mode, cb200_particle_buffer params, int n, const float* F_in, const float* log_jp_in, float* F_out, float* PF_out, float* log_jp_out, void* stream) {
+	if(n <= 0) return 0;
+	if(material < CB200_FIXED_COROTATED || material > CB200_NACC) return (int) cudaErrorInvalidValue;
+	test_stress_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t) stream>>>(material, mode, mat_of(params), n, F_in, log_jp_in, F_out, PF_out, log_jp_out);
+	return (int) cudaGetLastError();
+}
+// ParticleBuffer<M> defaults (particle_buffer.cuh:141-264) as the step driver sets them (engine.cu)
+void cb200_default_material(const cb200_config* cfg, int material, cb200_particle_buffer* out);
+}

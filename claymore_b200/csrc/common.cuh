@@ -103,6 +103,7 @@ struct StepState {
 	int prev_ebc;
 	int work_counter;       // dynamic block scheduler of g2p2g
 	int work_counter2;
+	int work_counter_mat[4];  // one block queue per material launch of a sub-step (all zeroed when the state rolls)
 	int error;              // sticky error bits (see cb200_sim_stats)
 	float dt, next_dt;
 	float max_vel_sq;       // max |v|^2 as float bits (non-negative => int compare is order preserving)

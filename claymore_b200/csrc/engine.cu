@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "g2p2g.cuh"
@@ -40,7 +41,9 @@ namespace {
 // Device-memory pool.  The reference frees and re-allocates its containers through raw cudaMalloc/cudaFree
 // (GmpmSimulator::DeviceAllocator, gmpm_simulator.cuh:40-51); multi-GB cudaFree/cudaMalloc pairs cost tens to hundreds
 // of milliseconds, so released blocks are kept (per device, exact size) and handed out again.  cb200_trim_pool() returns
-// everything to the driver.  Buffers exposed through CUDA IPC are never pooled.
+// everything to the driver.  Buffers exposed through CUDA IPC are pooled as well: a re-used buffer has the same IPC handle, and
+// the importing side keeps every mapping it has opened (IpcCache below), so a second simulator of a process costs neither a
+// cudaMalloc nor a cudaIpcOpenMemHandle (they were ~0.4 s of the 8-rank end-to-end time in round 1).
 class DevicePool {
 public:
 	cudaError_t alloc(void** p, size_t bytes) {
@@ -91,6 +94,28 @@ private:
 	std::multimap<std::pair<int, size_t>, void*> free_;
 };
 DevicePool g_pool;
+
+// mappings of peer buffers opened through CUDA IPC, kept for the life of the process (a handle can be opened once per process)
+class IpcCache {
+public:
+	cudaError_t open(void** p, const cudaIpcMemHandle_t& h) {
+		std::lock_guard<std::mutex> g(mu_);
+		const std::string key(reinterpret_cast<const char*>(&h), sizeof(h));
+		auto it = map_.find(key);
+		if(it != map_.end()) {
+			*p = it->second;
+			return cudaSuccess;
+		}
+		const cudaError_t e = cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess);
+		if(e == cudaSuccess) map_[key] = *p;
+		return e;
+	}
+
+private:
+	std::mutex mu_;
+	std::map<std::string, void*> map_;
+};
+IpcCache g_ipc;
 template<typename T>
 cudaError_t pool_alloc(T** p, size_t bytes) { return g_pool.alloc(reinterpret_cast<void**>(p), bytes); }
 
@@ -181,7 +206,7 @@ struct cb200_sim {
 	StepState* h_poll = nullptr;  // pinned
 	cudaEvent_t poll_event = nullptr;
 	bool poll_pending = false;
-	int steps_since_poll = 0;
+	int steps_since_poll = 15;  // the first sub-step polls
 	int grow_events = 0;
 };
 
@@ -245,7 +270,8 @@ G2P2GArgs make_g2p2g_args(cb200_sim* s, int material, int R, int halo_mode) {
 	a.grid = s->grid[0];
 	a.next_grid = s->grid[1];
 	a.error = &s->d_state->error;
-	a.work_counter = halo_mode == 1 ? &s->d_state->work_counter2 : &s->d_state->work_counter;
+	// one queue per launch: each material's launch of a sub-step pulls from its own counter
+	a.work_counter = halo_mode == 1 ? &s->d_state->work_counter2 : (halo_mode == 0 ? &s->d_state->work_counter_mat[material] : &s->d_state->work_counter);
 	if(s->desc.mgsp_world > 1 && halo_mode == 0) {
 		a.overlap_marks = s->part[R].overlap_marks;
 		a.peer_bno = s->peer_bno;
@@ -307,7 +333,7 @@ int enqueue_g2p2g(cb200_sim* s, int R, int halo_mode, cudaStream_t st = nullptr)
 			CK(cudaEventRecord(s->prof_events[s->prof_used].first, st));
 		}
 		G2P2GArgs b = a;
-		if(n_materials > 1) b.work_counter = nullptr;  // one queue per launch: several materials fall back to static striding
+		if(n_materials > 1 && halo_mode != 0) b.work_counter = nullptr;  // the split (halo / interior) launches share two counters: static striding
 		CK(launch_g2p2g(material, b, -1, st));
 		if(timed) CK(cudaEventRecord(s->prof_events[s->prof_used++].second, st));
 		++s->launches;
@@ -639,6 +665,12 @@ extern "C" {
 // (gmpm_simulator.cuh:283-300, 371-376, 404-411, 528-548), except that every live array keeps its contents (the reference
 // resizes the *next* buffers, whose contents are dead at that point of its loop; here the call may come at any sub-step
 // boundary).  The sub-step graphs are re-captured on the next step.
+void cb200_default_material(const cb200_config* cfg, int material, cb200_particle_buffer* out) {
+	if(!cfg || !out) return;
+	memset(out, 0, sizeof(*out));
+	default_material(*cfg, material, *out);
+}
+
 int cb200_sim_reserve(cb200_sim* s, int new_max_blocks) {
 	if(!s || new_max_blocks <= 0) return (int) cudaErrorInvalidValue;
 	if(new_max_blocks <= s->desc.max_blocks) return 0;
@@ -729,8 +761,7 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 	for(int i = 0; i < 2; ++i) {
 		int e = alloc_partition(s, s->part[i]);
 		if(e) return e;
-		// the next grid is exposed to the peers through CUDA IPC in MGSP mode: not pooled then
-		CK(s->desc.mgsp_world > 1 ? cudaMalloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)) : pool_alloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
+		CK(pool_alloc(&s->grid[i], (mb + 1) * kGridBlockFloats * sizeof(float)));
 		CK(cudaMemsetAsync(s->grid[i], 0, (mb + 1) * kGridBlockFloats * sizeof(float), s->stream));
 	}
 	{
@@ -747,7 +778,7 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 		CK(pool_alloc(&s->peer_overlap_count, (size_t) s->desc.mgsp_world * sizeof(int)));
 		CK(cudaMemsetAsync(s->peer_overlap_count, 0, (size_t) s->desc.mgsp_world * sizeof(int), s->stream));
 		s->inbox_layout = make_inbox_layout(s->desc.mgsp_world, s->desc.mgsp_halo_cap, desc->max_blocks);
-		CK(cudaMalloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
+		CK(pool_alloc(&s->inbox_local, inbox_bytes(s->inbox_layout)));
 		CK(cudaMemsetAsync(s->inbox_local, 0, inbox_bytes(s->inbox_layout), s->stream));
 		s->inbox_peer[s->desc.mgsp_rank] = s->inbox_local;
 		s->grid1_peer[s->desc.mgsp_rank] = s->grid[1];
@@ -799,10 +830,7 @@ int cb200_sim_destroy(cb200_sim* s) {
 	g_pool.release(s->d_state);
 	g_pool.release(s->peer_overlap_keys);
 	g_pool.release(s->peer_overlap_count);
-	for(int r = 0; r < kMaxRanks; ++r)
-		if(s->inbox_opened[r]) cudaIpcCloseMemHandle(s->inbox_peer[r]);
-	for(int r = 0; r < kMaxRanks; ++r)
-		if(s->grid1_opened[r]) cudaIpcCloseMemHandle(s->grid1_peer[r]);
+	// peer mappings stay open (IpcCache): the exporting rank pools the buffer, the next simulator maps the same handle
 	g_pool.release(s->peer_bno);
 	g_pool.release(s->inbox_local);
 	g_pool.release(s->mgsp_done);
@@ -1218,11 +1246,11 @@ int cb200_sim_mgsp_open_peers(cb200_sim* s, const void* handles) {
 		cudaIpcMemHandle_t h;
 		void* p = nullptr;
 		memcpy(&h, (const unsigned char*) handles + 128 * r, 64);
-		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		CK(g_ipc.open(&p, h));
 		s->inbox_peer[r] = (unsigned char*) p;
 		s->inbox_opened[r] = true;
 		memcpy(&h, (const unsigned char*) handles + 128 * r + 64, 64);
-		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		CK(g_ipc.open(&p, h));
 		s->grid1_peer[r] = (float*) p;
 		s->grid1_opened[r] = true;
 	}

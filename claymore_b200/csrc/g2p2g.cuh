@@ -338,52 +338,53 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
 					ab[d] = ((base[d] - 1) & 3) + 1;
 				}
-				// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d])
-				// sum-factorised over the separable weights: 288 FMA instead of 27 x 16 operations
-				float vel[3] = {0.f, 0.f, 0.f};
-				float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+				// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d]),
+				// sum-factorised over the separable weights and issued as packed FP32: a node's (vx, vy) is the aligned
+				// register pair its LDS.128 delivered, weights enter as broadcast scalars; 147 FFMA2/FFMA instead of 288 FFMA
+				float vel[3], A[9];
 				const int nbase = (ab[0] * 8 + ab[1]) * 8 + ab[2];
-				float wxx[3], wyx[3], wzx[3];
+				{
+					float wxx[3], wyx[3];
+					f2 wzp[3];  // (w_z[k], w_z[k] * (z_k - z_p))
 #pragma unroll
-				for(int i = 0; i < 3; ++i) {
-					wxx[i] = w[0][i] * (i * dx - lp[0]);
-					wyx[i] = w[1][i] * (i * dx - lp[1]);
-					wzx[i] = w[2][i] * (i * dx - lp[2]);
-				}
-#pragma unroll
-				for(int i = 0; i < 3; ++i) {
-					float R0 = 0.f, R1 = 0.f, R2 = 0.f, Y0 = 0.f, Y1 = 0.f, Y2 = 0.f, Z0 = 0.f, Z1 = 0.f, Z2 = 0.f;
-#pragma unroll
-					for(int j = 0; j < 3; ++j) {
-						const float4 v0 = sm.vel4[nbase + i * 64 + j * 8], v1 = sm.vel4[nbase + i * 64 + j * 8 + 1], v2 = sm.vel4[nbase + i * 64 + j * 8 + 2];
-						const float P0 = w[2][0] * v0.x + w[2][1] * v1.x + w[2][2] * v2.x;
-						const float P1 = w[2][0] * v0.y + w[2][1] * v1.y + w[2][2] * v2.y;
-						const float P2 = w[2][0] * v0.z + w[2][1] * v1.z + w[2][2] * v2.z;
-						const float Q0 = wzx[0] * v0.x + wzx[1] * v1.x + wzx[2] * v2.x;
-						const float Q1 = wzx[0] * v0.y + wzx[1] * v1.y + wzx[2] * v2.y;
-						const float Q2 = wzx[0] * v0.z + wzx[1] * v1.z + wzx[2] * v2.z;
-						R0 += w[1][j] * P0;
-						R1 += w[1][j] * P1;
-						R2 += w[1][j] * P2;
-						Y0 += wyx[j] * P0;
-						Y1 += wyx[j] * P1;
-						Y2 += wyx[j] * P2;
-						Z0 += w[1][j] * Q0;
-						Z1 += w[1][j] * Q1;
-						Z2 += w[1][j] * Q2;
+					for(int i = 0; i < 3; ++i) {
+						wxx[i] = w[0][i] * (i * dx - lp[0]);
+						wyx[i] = w[1][i] * (i * dx - lp[1]);
+						wzp[i] = mk2(w[2][i], w[2][i] * (i * dx - lp[2]));
 					}
-					vel[0] += w[0][i] * R0;
-					vel[1] += w[0][i] * R1;
-					vel[2] += w[0][i] * R2;
-					A[0] += wxx[i] * R0;
-					A[1] += wxx[i] * R1;
-					A[2] += wxx[i] * R2;
-					A[3] += w[0][i] * Y0;
-					A[4] += w[0][i] * Y1;
-					A[5] += w[0][i] * Y2;
-					A[6] += w[0][i] * Z0;
-					A[7] += w[0][i] * Z1;
-					A[8] += w[0][i] * Z2;
+					const f2 z2 = mk2(0.f, 0.f);
+					f2 velxy = z2, A01 = z2, A34 = z2, A67 = z2, vzA8 = z2;
+					float A2 = 0.f, A5 = 0.f;
+#pragma unroll
+					for(int i = 0; i < 3; ++i) {
+						f2 Rxy = z2, Yxy = z2, Zxy = z2, RzZz = z2;
+						float Yz = 0.f;
+#pragma unroll
+						for(int j = 0; j < 3; ++j) {
+							const float4 v0 = sm.vel4[nbase + i * 64 + j * 8], v1 = sm.vel4[nbase + i * 64 + j * 8 + 1], v2 = sm.vel4[nbase + i * 64 + j * 8 + 2];
+							f2 Pxy = mul2(mk2(v0.x, v0.y), wzp[0].x), Qxy = mul2(mk2(v0.x, v0.y), wzp[0].y), PzQz = mul2(wzp[0], v0.z);
+							Pxy = fma2(mk2(v1.x, v1.y), wzp[1].x, Pxy);
+							Qxy = fma2(mk2(v1.x, v1.y), wzp[1].y, Qxy);
+							PzQz = fma2(wzp[1], v1.z, PzQz);
+							Pxy = fma2(mk2(v2.x, v2.y), wzp[2].x, Pxy);
+							Qxy = fma2(mk2(v2.x, v2.y), wzp[2].y, Qxy);
+							PzQz = fma2(wzp[2], v2.z, PzQz);
+							Rxy = fma2(Pxy, w[1][j], Rxy);
+							Yxy = fma2(Pxy, wyx[j], Yxy);
+							Zxy = fma2(Qxy, w[1][j], Zxy);
+							RzZz = fma2(PzQz, w[1][j], RzZz);
+							Yz = fmaf(wyx[j], PzQz.x, Yz);
+						}
+						velxy = fma2(Rxy, w[0][i], velxy);
+						A01 = fma2(Rxy, wxx[i], A01);
+						A34 = fma2(Yxy, w[0][i], A34);
+						A67 = fma2(Zxy, w[0][i], A67);
+						vzA8 = fma2(RzZz, w[0][i], vzA8);
+						A2 = fmaf(wxx[i], RzZz.x, A2);
+						A5 = fmaf(w[0][i], Yz, A5);
+					}
+					vel[0] = velxy.x, vel[1] = velxy.y, vel[2] = vzA8.x;
+					A[0] = A01.x, A[1] = A01.y, A[2] = A2, A[3] = A34.x, A[4] = A34.y, A[5] = A5, A[6] = A67.x, A[7] = A67.y, A[8] = vzA8.y;
 				}
 #pragma unroll
 				for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
@@ -469,12 +470,16 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						dbin[12 * 32] = log_jp;
 					}
 				}
+				// D = (A m - stress new_dt) D_inv dx   (the affine momentum matrix in units of the cell size, column-major c + 3d)
+				{
+					const float ka = mass * d_inv * dx, ks = -new_dt * d_inv * dx;
 #pragma unroll
-				for(int d = 0; d < 9; ++d) contrib[d] = (A[d] * mass - contrib[d] * new_dt) * d_inv;
+					for(int d = 0; d < 9; ++d) contrib[d] = fmaf(A[d], ka, contrib[d] * ks);
+				}
 
 				// ---- re-bucket, part 2: store the advection tag into the claimed slot --------------------
 #pragma unroll
-				for(int d = 0; d < 3; ++d) lp[d] = pos[d] - nb[d] * dx;
+				for(int d = 0; d < 3; ++d) lp[d] = (pos[d] - nb[d] * dx) * dx_inv;
 				if(rb_slot >= 0) {
 					if(rb_slot >= cfg.max_ppc) {
 						atomicSub(M.next.cell_particle_counts + rb_cell, 1);
@@ -502,13 +507,15 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					code |= kRecMover;
 					sm.movers[atomicAdd(&sm.nmovers, 1)] = (unsigned short) slot;
 				}
+				// momentum of node (i, j, k) of the particle's stencil: q + i D[:,0] + j D[:,1] + k D[:,2], with q = m v - D x_p
 				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
 				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
 				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
-				sm.rec[0][rs] = make_float4(lp[0] * dx_inv, lp[1] * dx_inv, lp[2] * dx_inv, __int_as_float(code));
-				sm.rec[1][rs] = make_float4(q0, q1, q2, contrib[0] * dx);
-				sm.rec[2][rs] = make_float4(contrib[1] * dx, contrib[2] * dx, contrib[3] * dx, contrib[4] * dx);
-				sm.rec[3][rs] = make_float4(contrib[5] * dx, contrib[6] * dx, contrib[7] * dx, contrib[8] * dx);
+				// record layout chosen for phase 2's packed arithmetic: (y, z) and the (component 1, component 2) terms are aligned pairs
+				sm.rec[0][rs] = make_float4(lp[1], lp[2], lp[0], __int_as_float(code));
+				sm.rec[1][rs] = make_float4(q1, q2, contrib[1], contrib[2]);
+				sm.rec[2][rs] = make_float4(contrib[4], contrib[5], contrib[7], contrib[8]);
+				sm.rec[3][rs] = make_float4(q0, contrib[0], contrib[3], contrib[6]);
 				// counting sort by the cell the particle came from (its accumulation home)
 				const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
 				const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);
@@ -565,34 +572,54 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				float pa, pb, pc;
 				bspline_poly(sl, pa, pb, pc);
 				const float fi = (float) sl;
-				float acc[9][4];
+				// accumulators as packed pairs: (mass, momentum x), (momentum y, momentum z) of the 9 nodes of this x-slice
+				f2 acc01[9], acc23[9];
 #pragma unroll
-				for(int n9 = 0; n9 < 9; ++n9) acc[n9][0] = acc[n9][1] = acc[n9][2] = acc[n9][3] = 0.f;
+				for(int n9 = 0; n9 < 9; ++n9) acc01[n9] = acc23[n9] = mk2(0.f, 0.f);
+				const f2 c01 = mk2(0.f, 1.f);
 				for(int p = 0; p < n; ++p) {
 					const int slot = rec_slot(sm.idx[st + p]);
-					const float4 r0 = sm.rec[0][slot];
+					const float4 r0 = sm.rec[0][slot];  // (y, z, x, code)
 					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
 					const float4 r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
-					const float wx = pa + r0.x * (pb + pc * r0.x);
-					float wy[3], wz[3];
-					bspline_weights(r0.y, wy[0], wy[1], wy[2]);
-					bspline_weights(r0.z, wz[0], wz[1], wz[2]);
-					// D (= contrib * dx, column-major c + 3d): r1.w r2.x r2.y | r2.z r2.w r3.x | r3.y r3.z r3.w
-					const float t0 = r1.x + fi * r1.w, t1 = r1.y + fi * r2.x, t2 = r1.z + fi * r2.y;
+					const float wx = pa + r0.z * (pb + pc * r0.z);
+					// B-spline weights of y and z in one packed pass: wyz[i] = (w_y[i], w_z[i])
+					f2 wyz[3];
+					{
+						const f2 d = mk2(r0.x, r0.y);
+						const f2 e = add2(dup2(1.5f), mul2(d, -1.f));
+						wyz[0] = mul2(mul2(e, e), 0.5f);
+						const f2 g = add2(d, dup2(-1.f));
+						wyz[1] = fma2(mul2(g, -1.f), g, dup2(0.75f));
+						const f2 h = add2(g, dup2(0.5f));
+						wyz[2] = mul2(mul2(h, h), 0.5f);
+					}
+					// (1, momentum x) and (momentum y, momentum z) at node (sl, 0, 0) of the stencil
+					f2 a0 = mk2(1.f, fmaf(fi, r3.y, r3.x));
+					f2 b0 = fma2(mk2(r1.z, r1.w), fi, mk2(r1.x, r1.y));
 #pragma unroll
 					for(int j = 0; j < 3; ++j) {
-						const float wxy = wx * wy[j];
-						const float u0 = t0 + j * r2.z, u1 = t1 + j * r2.w, u2 = t2 + j * r3.x;
+						const float wxy = wx * wyz[j].x;
+						f2 ak = a0, bk = b0;
 #pragma unroll
 						for(int k = 0; k < 3; ++k) {
-							const float W = wxy * wz[k];
-							acc[j * 3 + k][0] += W;
-							acc[j * 3 + k][1] += W * (u0 + k * r3.y);
-							acc[j * 3 + k][2] += W * (u1 + k * r3.z);
-							acc[j * 3 + k][3] += W * (u2 + k * r3.w);
+							const float W = wxy * wyz[k].y;
+							acc01[j * 3 + k] = fma2(ak, W, acc01[j * 3 + k]);
+							acc23[j * 3 + k] = fma2(bk, W, acc23[j * 3 + k]);
+							if(k < 2) {
+								ak = fma2(c01, r3.w, ak);
+								bk = add2(bk, mk2(r2.z, r2.w));
+							}
+						}
+						if(j < 2) {
+							a0 = fma2(c01, r3.z, a0);
+							b0 = add2(b0, mk2(r2.x, r2.y));
 						}
 					}
 				}
+				float acc[9][4];
+#pragma unroll
+				for(int n9 = 0; n9 < 9; ++n9) acc[n9][0] = acc01[n9].x, acc[n9][1] = acc01[n9].y, acc[n9][2] = acc23[n9].x, acc[n9][3] = acc23[n9].y;
 				// Registers -> arena by plain read-add-write, no atomics (a shared float atomicAdd is a compare-and-swap loop: 36 per
 				// thread were 60 % of the kernel's shared-memory wavefronts).  All lanes of a warp execute the same stencil offset
 				// (j, k) on different cells, i.e. on different nodes, and a thread only writes the node plane X of its slice, so
@@ -645,18 +672,18 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					const int code = __float_as_int(r0.w);
 					float pa, pb, pc;
 					bspline_poly(i, pa, pb, pc);
-					const float wx = pa + r0.x * (pb + pc * r0.x);
+					const float wx = pa + r0.z * (pb + pc * r0.z);
 					bspline_poly(j, pa, pb, pc);
-					const float wy = pa + r0.y * (pb + pc * r0.y);
+					const float wy = pa + r0.x * (pb + pc * r0.x);
 					bspline_poly(k, pa, pb, pc);
-					const float wz = pa + r0.z * (pb + pc * r0.z);
+					const float wz = pa + r0.y * (pb + pc * r0.y);
 					const float W = wx * wy * wz;
 					const float fi = (float) i, fj = (float) j, fk = (float) k;
 					const int o = acc_off_x((code & 7) + i) + acc_off_y(((code >> 3) & 7) + j) + acc_off_z(((code >> 6) & 7) + k);
 					atomicAdd(&sm.acc[o], mass * W);
-					atomicAdd(&sm.acc[o + 64], W * (r1.x + fi * r1.w + fj * r2.z + fk * r3.y));
-					atomicAdd(&sm.acc[o + 128], W * (r1.y + fi * r2.x + fj * r2.w + fk * r3.z));
-					atomicAdd(&sm.acc[o + 192], W * (r1.z + fi * r2.y + fj * r3.x + fk * r3.w));
+					atomicAdd(&sm.acc[o + 64], W * (r3.x + fi * r3.y + fj * r3.z + fk * r3.w));
+					atomicAdd(&sm.acc[o + 128], W * (r1.x + fi * r1.z + fj * r2.x + fk * r2.z));
+					atomicAdd(&sm.acc[o + 192], W * (r1.y + fi * r1.w + fj * r2.y + fk * r2.w));
 				}
 			}
 		}

@@ -11,6 +11,21 @@
 
 namespace cb200 {
 
+// ------------------------------------------------------------------------------------------------
+// packed FP32 (sm_100a: fma.rn.f32x2 / FFMA2, FMUL2, FADD2).  One instruction does two FP32 operations on an aligned register
+// pair; an operand may also be ONE register broadcast to both halves (SASS `Rn.F32`), so a scalar weight costs no packing.
+// The scalar FP32 pipe issues one warp-FFMA per two cycles per SM sub-partition: the packed forms are the only way to the
+// nominal FP32 rate, and they halve the issue slots of the separable-weight arithmetic of G2P / P2G.
+// ------------------------------------------------------------------------------------------------
+using f2 = float2;
+__device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 fma2(f2 a, float s, f2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+
 // quadratic B-spline weights of the 3 nodes covering local position p in [0.5dx, 1.5dx)
 __device__ __forceinline__ void bspline_weights(float p_times_dxinv, float& w0, float& w1, float& w2) {
 	float d = p_times_dxinv;

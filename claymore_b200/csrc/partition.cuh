@@ -451,6 +451,7 @@ __device__ __forceinline__ void finalize_step(const FinalizeArgs& a) {
 	s->max_vel_sq = a.next_max_vel ? *a.next_max_vel : 0.f;
 	s->work_counter = 0;
 	s->work_counter2 = 0;
+	for(int m = 0; m < 4; ++m) s->work_counter_mat[m] = 0;
 	s->steps += 1;
 }
 __global__ void finalize_step_kernel(const FinalizeArgs a) {

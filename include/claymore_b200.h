@@ -221,6 +221,16 @@ CB200_API int cb200_sim_mgsp_set_peers(cb200_sim* sim, void* const* inbox_ptrs_b
 /* halo statistics of the current partition (synchronises): blocks shared with each rank, halo particle blocks */
 CB200_API int cb200_sim_mgsp_halo_counts(cb200_sim* sim, int* shared_blocks_by_rank, int* halo_particle_blocks);
 
+/* ------------------------------------------------------------------------------------------------
+ * Test-only hooks (used by tests/, not part of the drop-in surface): the device 3x3 SVD and constitutive models of g2p2g on
+ * caller-supplied DEVICE vectors, against math::svd (Library/MnBase/Math/Matrix/svd.cuh:28-1124) and compute_stress<M>
+ * (Projects/GMPM/constitutive_models.cuh:36-335).  F: float[9n] column-major; mode 0 = the path g2p2g takes, 1 = FIXED_COROTATED via SVD.
+ * ---------------------------------------------------------------------------------------------- */
+CB200_API int cb200_test_svd3(int n, const float* F, float* U, float* S, float* V, void* stream);
+CB200_API int cb200_test_stress(int material, int mode, cb200_particle_buffer params, int n, const float* F_in, const float* log_jp_in, float* F_out, float* PF_out, float* log_jp_out, void* stream);
+/* ParticleBuffer<M> default parameters (particle_buffer.cuh:141-264) for `material` on the grid of `cfg` (pointers zero) */
+CB200_API void cb200_default_material(const cb200_config* cfg, int material, cb200_particle_buffer* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_binding_signatures_cover_header():
     from claymore_b200 import _capi
-    bound = set(_capi._SIGNATURES) | {"cb200_version", "cb200_error_string", "cb200_sim_launch_count"}
+    bound = set(_capi._SIGNATURES) | {"cb200_version", "cb200_error_string", "cb200_sim_launch_count", "cb200_default_material"}
     assert set(_declared_symbols()) <= bound, sorted(set(_declared_symbols()) - bound)
 
 
