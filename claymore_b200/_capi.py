@@ -154,7 +154,11 @@ def lib():
                              "claymore_b200 has no CPU fallback.")
         L = C.CDLL(_LIB)
         for name, args in _SIGNATURES.items():
-            fn = getattr(L, name)
+            fn = getattr(L, name, None)
+            if fn is None:
+                if _VARIANT:   # experiment builds of older sources may lack newer entry points
+                    continue
+                raise CB200Error(f"{_LIB} does not export {name}: rebuild it (claymore_b200.build_library(force=True))")
             fn.argtypes = args
             fn.restype = C.c_int
         L.cb200_sim_launch_count.argtypes = [_P]

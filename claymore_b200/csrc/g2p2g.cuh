@@ -83,7 +83,7 @@ __device__ __forceinline__ int acc_off_y(int Y) { return ((Y >> 2) << 1) * 256 +
 __device__ __forceinline__ int acc_off_z(int Z) { return (Z >> 2) * 256 + (Z & 3); }
 
 struct G2P2GSmem {
-	float4 vel4[512];                // node-major velocity arena, index (X*8+Y)*8+Z
+	float4 vel4[512];                // node-major velocity arena (v_y, v_z, v_x, gather tag in flight), index (X*8+Y)*8+Z
 	float acc[8 * 256];              // accumulation arena (grid-block layout)
 	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads; 6 KiB of quad 1 double as the TMA landing
 	                                 // zone (8 blocks x 3 channels x 64 cells) while a block's neighbourhood is staged
@@ -246,8 +246,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				const int bi = ((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2);
 				const int o = bi * 192 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3));
 				const bool ok = (valid >> bi) & 1u;  // w holds a gather tag in flight: write x, y, z only
-				*reinterpret_cast<float2*>(&sm.vel4[n].x) = ok ? make_float2(velsoa[o], velsoa[o + 64]) : make_float2(0.f, 0.f);
-				sm.vel4[n].z = ok ? velsoa[o + 128] : 0.f;
+				// node layout (v_y, v_z, v_x, -): G2P's packed arithmetic pairs the components (1, 2)
+				*reinterpret_cast<float2*>(&sm.vel4[n].x) = ok ? make_float2(velsoa[o + 64], velsoa[o + 128]) : make_float2(0.f, 0.f);
+				sm.vel4[n].z = ok ? velsoa[o] : 0.f;
 			}
 		}
 		__syncthreads();  // S2: vel4, nbr, prevno, srcbin
@@ -335,59 +336,71 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				for(int d = 0; d < 3; ++d) {
 					base[d] = cell_index(cfg, pos[d]) - 1;
 					lp[d] = pos[d] - base[d] * dx;
-					bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
+					if(d > 0) bspline_weights(lp[d] * dx_inv, w[d][0], w[d][1], w[d][2]);
 					ab[d] = ((base[d] - 1) & 3) + 1;
 				}
 				// G2P: velocity and APIC matrix (A as in the reference: sum W v (x_i - x_p)^T, column-major A[c + 3d]),
-				// sum-factorised over the separable weights and issued as packed FP32: a node's (vx, vy) is the aligned
-				// register pair its LDS.128 delivered, weights enter as broadcast scalars; 147 FFMA2/FFMA instead of 288 FFMA
-				float vel[3], A[9];
-				const int nbase = (ab[0] * 8 + ab[1]) * 8 + ab[2];
+				// sum-factorised over the separable weights and issued as packed FP32: a node's (v_y, v_z) is the aligned register
+				// pair its LDS.128 delivered, weights enter as broadcast scalars: 132 FFMA2 + 15 FFMA instead of 288 FFMA.
+				// A, F and the stress stay in the packed 3x3 form (rows 1-2 of a column = one pair) up to the staged record.
+				float velx;
+				f2 velyz;
+				M3p A;
 				{
-					float wxx[3], wyx[3];
+					float wyx[3];
 					f2 wzp[3];  // (w_z[k], w_z[k] * (z_k - z_p))
 #pragma unroll
 					for(int i = 0; i < 3; ++i) {
-						wxx[i] = w[0][i] * (i * dx - lp[0]);
 						wyx[i] = w[1][i] * (i * dx - lp[1]);
 						wzp[i] = mk2(w[2][i], w[2][i] * (i * dx - lp[2]));
 					}
 					const f2 z2 = mk2(0.f, 0.f);
-					f2 velxy = z2, A01 = z2, A34 = z2, A67 = z2, vzA8 = z2;
-					float A2 = 0.f, A5 = 0.f;
-#pragma unroll
-					for(int i = 0; i < 3; ++i) {
-						f2 Rxy = z2, Yxy = z2, Zxy = z2, RzZz = z2;
-						float Yz = 0.f;
+					f2 vyz = z2, A12 = z2, A45 = z2, A78 = z2, vxA6 = z2;
+					float A0 = 0.f, A3 = 0.f;
+					const float4* vp = &sm.vel4[(ab[0] * 8 + ab[1]) * 8 + ab[2]];
+					const float dxn = lp[0] * dx_inv;
+					// the x planes are a real loop (its weight comes from the polynomial form): unrolled, the scheduler hoists all 27
+					// LDS.128 of the stencil and spills
+#pragma unroll 1
+					for(int i = 0; i < 3; ++i, vp += 64) {
+						float pa, pb, pc;
+						bspline_poly(i, pa, pb, pc);
+						const float wx = pa + dxn * (pb + pc * dxn);
+						const float wxx = wx * ((float) i * dx - lp[0]);
+						f2 Ryz = z2, Yyz = z2, Zyz = z2, RxZx = z2;
+						float Yx = 0.f;
 #pragma unroll
 						for(int j = 0; j < 3; ++j) {
-							const float4 v0 = sm.vel4[nbase + i * 64 + j * 8], v1 = sm.vel4[nbase + i * 64 + j * 8 + 1], v2 = sm.vel4[nbase + i * 64 + j * 8 + 2];
-							f2 Pxy = mul2(mk2(v0.x, v0.y), wzp[0].x), Qxy = mul2(mk2(v0.x, v0.y), wzp[0].y), PzQz = mul2(wzp[0], v0.z);
-							Pxy = fma2(mk2(v1.x, v1.y), wzp[1].x, Pxy);
-							Qxy = fma2(mk2(v1.x, v1.y), wzp[1].y, Qxy);
-							PzQz = fma2(wzp[1], v1.z, PzQz);
-							Pxy = fma2(mk2(v2.x, v2.y), wzp[2].x, Pxy);
-							Qxy = fma2(mk2(v2.x, v2.y), wzp[2].y, Qxy);
-							PzQz = fma2(wzp[2], v2.z, PzQz);
-							Rxy = fma2(Pxy, w[1][j], Rxy);
-							Yxy = fma2(Pxy, wyx[j], Yxy);
-							Zxy = fma2(Qxy, w[1][j], Zxy);
-							RzZz = fma2(PzQz, w[1][j], RzZz);
-							Yz = fmaf(wyx[j], PzQz.x, Yz);
+							const float4 v0 = vp[j * 8], v1 = vp[j * 8 + 1], v2 = vp[j * 8 + 2];
+							f2 Pyz = mul2(mk2(v0.x, v0.y), wzp[0].x), Qyz = mul2(mk2(v0.x, v0.y), wzp[0].y), PxQx = mul2(wzp[0], v0.z);
+							Pyz = fma2(mk2(v1.x, v1.y), wzp[1].x, Pyz);
+							Qyz = fma2(mk2(v1.x, v1.y), wzp[1].y, Qyz);
+							PxQx = fma2(wzp[1], v1.z, PxQx);
+							Pyz = fma2(mk2(v2.x, v2.y), wzp[2].x, Pyz);
+							Qyz = fma2(mk2(v2.x, v2.y), wzp[2].y, Qyz);
+							PxQx = fma2(wzp[2], v2.z, PxQx);
+							Ryz = fma2(Pyz, w[1][j], Ryz);
+							Yyz = fma2(Pyz, wyx[j], Yyz);
+							Zyz = fma2(Qyz, w[1][j], Zyz);
+							RxZx = fma2(PxQx, w[1][j], RxZx);
+							Yx = fmaf(wyx[j], PxQx.x, Yx);
 						}
-						velxy = fma2(Rxy, w[0][i], velxy);
-						A01 = fma2(Rxy, wxx[i], A01);
-						A34 = fma2(Yxy, w[0][i], A34);
-						A67 = fma2(Zxy, w[0][i], A67);
-						vzA8 = fma2(RzZz, w[0][i], vzA8);
-						A2 = fmaf(wxx[i], RzZz.x, A2);
-						A5 = fmaf(w[0][i], Yz, A5);
+						vyz = fma2(Ryz, wx, vyz);
+						A12 = fma2(Ryz, wxx, A12);
+						A45 = fma2(Yyz, wx, A45);
+						A78 = fma2(Zyz, wx, A78);
+						vxA6 = fma2(RxZx, wx, vxA6);
+						A0 = fmaf(wxx, RxZx.x, A0);
+						A3 = fmaf(wx, Yx, A3);
 					}
-					vel[0] = velxy.x, vel[1] = velxy.y, vel[2] = vzA8.x;
-					A[0] = A01.x, A[1] = A01.y, A[2] = A2, A[3] = A34.x, A[4] = A34.y, A[5] = A5, A[6] = A67.x, A[7] = A67.y, A[8] = vzA8.y;
+					velx = vxA6.x;
+					velyz = vyz;
+					A.s[0] = A0, A.s[1] = A3, A.s[2] = vxA6.y;
+					A.p[0] = A12, A.p[1] = A45, A.p[2] = A78;
 				}
-#pragma unroll
-				for(int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+				pos[0] = fmaf(velx, dt, pos[0]);
+				pos[1] = fmaf(velyz.x, dt, pos[1]);
+				pos[2] = fmaf(velyz.y, dt, pos[2]);
 
 				// ---- re-bucket (add_advection), part 1: claim a slot in the new cell NOW so that the round trip of the
 				// global atomic overlaps the deformation-gradient / stress arithmetic below; the tag is stored after it
@@ -419,62 +432,80 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					}
 				}
 
-				float contrib[9];
+				M3p S;  // stress contribution P F^T vol (fluid: the Cauchy-like term of :474-516)
 				float* __restrict__ dbin = M.next.bins + ((size_t) dst_bin0 + (pidib >> 5)) * BINF + (pidib & 31);
 				if constexpr(MAT == CB200_J_FLUID) {
 					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
 					float J = sm.rec[1][rs].x;
-					J += (A[0] + A[4] + A[8]) * dt * d_inv * J;
+					J += (A.s[0] + A.p[1].x + A.p[2].y) * dt * d_inv * J;
 					if(J < 0.1f) J = 0.1f;
 					const float voln = J * M.mat.volume;
 					const float pressure = M.mat.bulk * (powf(J, -M.mat.gamma) - 1.f);
 					const float vs = d_inv * M.mat.viscosity;
-					contrib[0] = ((A[0] + A[0]) * vs - pressure) * voln;
-					contrib[1] = (A[1] + A[3]) * vs * voln;
-					contrib[2] = (A[2] + A[6]) * vs * voln;
-					contrib[3] = contrib[1];
-					contrib[4] = ((A[4] + A[4]) * vs - pressure) * voln;
-					contrib[5] = (A[5] + A[7]) * vs * voln;
-					contrib[6] = contrib[2];
-					contrib[7] = contrib[5];
-					contrib[8] = ((A[8] + A[8]) * vs - pressure) * voln;
+					const float s01 = (A.p[0].x + A.s[1]) * vs * voln, s02 = (A.p[0].y + A.s[2]) * vs * voln, s12 = (A.p[1].y + A.p[2].x) * vs * voln;
+					S.s[0] = ((A.s[0] + A.s[0]) * vs - pressure) * voln;
+					S.p[0] = mk2(s01, s02);
+					S.s[1] = s01;
+					S.p[1] = mk2(((A.p[1].x + A.p[1].x) * vs - pressure) * voln, s12);
+					S.s[2] = s02;
+					S.p[2] = mk2(s12, ((A.p[2].y + A.p[2].y) * vs - pressure) * voln);
 					dbin[0] = pos[0];
 					dbin[32] = pos[1];
 					dbin[64] = pos[2];
 					dbin[96] = J;
 				} else {
-					float Fo[9], F[9], G[9];
 					cp_async_wait<1>();  // group A has landed (group B may still be in flight)
 					const float4 fa = sm.rec[1][rs], fb = sm.rec[2][rs], fc = sm.rec[3][rs];
-					Fo[0] = fa.x, Fo[1] = fa.y, Fo[2] = fa.z, Fo[3] = fa.w, Fo[4] = fb.x, Fo[5] = fb.y, Fo[6] = fb.z, Fo[7] = fb.w, Fo[8] = fc.x;
+					const float Fo[9] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x};
+					// F <- (I + A dt D_inv) F
 					const float sc = dt * d_inv;
+					M3p G, F;
+					G.s[0] = fmaf(A.s[0], sc, 1.f), G.s[1] = A.s[1] * sc, G.s[2] = A.s[2] * sc;
+					G.p[0] = mul2(A.p[0], sc);
+					G.p[1] = fma2(A.p[1], sc, mk2(1.f, 0.f));
+					G.p[2] = fma2(A.p[2], sc, mk2(0.f, 1.f));
 #pragma unroll
-					for(int d = 0; d < 9; ++d) G[d] = A[d] * sc + ((d & 3) ? 0.f : 1.f);
-#pragma unroll
-					for(int c = 0; c < 3; ++c)
-#pragma unroll
-						for(int r = 0; r < 3; ++r) F[r + 3 * c] = G[r] * Fo[3 * c] + G[r + 3] * Fo[3 * c + 1] + G[r + 6] * Fo[3 * c + 2];
+					for(int c = 0; c < 3; ++c) {
+						F.p[c] = fma2(G.p[2], Fo[3 * c + 2], fma2(G.p[1], Fo[3 * c + 1], mul2(G.p[0], Fo[3 * c])));
+						F.s[c] = fmaf(G.s[2], Fo[3 * c + 2], fmaf(G.s[1], Fo[3 * c + 1], G.s[0] * Fo[3 * c]));
+					}
 					dbin[0] = pos[0];
 					dbin[32] = pos[1];
 					dbin[64] = pos[2];
 					if constexpr(MAT == CB200_FIXED_COROTATED) {
 #pragma unroll
-						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
-						stress_fixed_corotated_polar(M.mat, F, contrib);
+						for(int c = 0; c < 3; ++c) {
+							dbin[(3 + 3 * c) * 32] = F.s[c];
+							dbin[(4 + 3 * c) * 32] = F.p[c].x;
+							dbin[(5 + 3 * c) * 32] = F.p[c].y;
+						}
+						if(!stress_fixed_corotated_polar_packed(M.mat, F, S)) {
+							float Fa[9], PFa[9];
+							m3p_to_array(F, Fa);
+							stress_fixed_corotated(M.mat, Fa, PFa);
+							S = m3p_from_array(PFa);
+						}
 					} else {
 						float log_jp = fc.y;
-						if constexpr(MAT == CB200_SAND) stress_sand(M.mat, F, contrib, log_jp);
-						else stress_nacc(M.mat, F, contrib, log_jp);
+						float Fa[9], PFa[9];
+						m3p_to_array(F, Fa);
+						if constexpr(MAT == CB200_SAND) stress_sand(M.mat, Fa, PFa, log_jp);
+						else stress_nacc(M.mat, Fa, PFa, log_jp);
 #pragma unroll
-						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = F[d];
+						for(int d = 0; d < 9; ++d) dbin[(3 + d) * 32] = Fa[d];
 						dbin[12 * 32] = log_jp;
+						S = m3p_from_array(PFa);
 					}
 				}
 				// D = (A m - stress new_dt) D_inv dx   (the affine momentum matrix in units of the cell size, column-major c + 3d)
+				M3p D;
 				{
 					const float ka = mass * d_inv * dx, ks = -new_dt * d_inv * dx;
 #pragma unroll
-					for(int d = 0; d < 9; ++d) contrib[d] = fmaf(A[d], ka, contrib[d] * ks);
+					for(int c = 0; c < 3; ++c) {
+						D.s[c] = fmaf(A.s[c], ka, S.s[c] * ks);
+						D.p[c] = fma2(A.p[c], ka, mul2(S.p[c], ks));
+					}
 				}
 
 				// ---- re-bucket, part 2: store the advection tag into the claimed slot --------------------
@@ -508,14 +539,13 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					sm.movers[atomicAdd(&sm.nmovers, 1)] = (unsigned short) slot;
 				}
 				// momentum of node (i, j, k) of the particle's stencil: q + i D[:,0] + j D[:,1] + k D[:,2], with q = m v - D x_p
-				const float q0 = mass * vel[0] - (contrib[0] * lp[0] + contrib[3] * lp[1] + contrib[6] * lp[2]);
-				const float q1 = mass * vel[1] - (contrib[1] * lp[0] + contrib[4] * lp[1] + contrib[7] * lp[2]);
-				const float q2 = mass * vel[2] - (contrib[2] * lp[0] + contrib[5] * lp[1] + contrib[8] * lp[2]);
+				const float q0 = fmaf(mass, velx, -fmaf(D.s[2], lp[2], fmaf(D.s[1], lp[1], D.s[0] * lp[0])));
+				const f2 q12 = fma2(D.p[2], -lp[2], fma2(D.p[1], -lp[1], fma2(D.p[0], -lp[0], mul2(velyz, mass))));
 				// record layout chosen for phase 2's packed arithmetic: (y, z) and the (component 1, component 2) terms are aligned pairs
 				sm.rec[0][rs] = make_float4(lp[1], lp[2], lp[0], __int_as_float(code));
-				sm.rec[1][rs] = make_float4(q1, q2, contrib[1], contrib[2]);
-				sm.rec[2][rs] = make_float4(contrib[4], contrib[5], contrib[7], contrib[8]);
-				sm.rec[3][rs] = make_float4(q0, contrib[0], contrib[3], contrib[6]);
+				sm.rec[1][rs] = make_float4(q12.x, q12.y, D.p[0].x, D.p[0].y);
+				sm.rec[2][rs] = make_float4(D.p[1].x, D.p[1].y, D.p[2].x, D.p[2].y);
+				sm.rec[3][rs] = make_float4(q0, D.s[0], D.s[1], D.s[2]);
 				// counting sort by the cell the particle came from (its accumulation home)
 				const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
 				const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);

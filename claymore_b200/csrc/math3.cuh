@@ -20,11 +20,19 @@ namespace cb200 {
 using f2 = float2;
 __device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ f2 dup2(float a) { return make_float2(a, a); }
+#ifndef CB200_NO_FFMA2
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 fma2(f2 a, float s, f2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ f2 mul2(f2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+#else  // A/B build: the same arithmetic issued as scalar FFMA / FMUL / FADD (csrc/Makefile `variants`)
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ f2 fma2(f2 a, float s, f2 c) { return make_float2(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ f2 mul2(f2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
 
 // quadratic B-spline weights of the 3 nodes covering local position p in [0.5dx, 1.5dx)
 __device__ __forceinline__ void bspline_weights(float p_times_dxinv, float& w0, float& w1, float& w2) {
@@ -283,7 +291,7 @@ __device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const
 			d2 = fmaf(d, d, d2);
 			R[i] = r;
 		}
-		if(d2 < 1e-13f) {
+		if(d2 < 2e-8f) {  // quadratic contraction: the step after this one would be below FP32 rounding
 			ok = true;
 			break;
 		}
@@ -301,6 +309,97 @@ __device__ __forceinline__ void stress_fixed_corotated_polar(const Mat& m, const
 	for(int c = 0; c < 3; ++c)
 #pragma unroll
 		for(int r = 0; r < 3; ++r) PF[r + 3 * c] = mu2v * (D[r] * F[c] + D[r + 3] * F[c + 3] + D[r + 6] * F[c + 6]) + ((r == c) ? iso : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 matrix in packed form (column-major m[r + 3c]): per column the rows (1, 2) as an aligned pair, row 0 as a scalar.
+// g2p2g keeps the APIC matrix, F and the stress in this form from the G2P accumulators to the staged P2G record.
+// ------------------------------------------------------------------------------------------------
+struct M3p {
+	float s[3];  // m[0 + 3c]
+	f2 p[3];     // (m[1 + 3c], m[2 + 3c])
+	__device__ __forceinline__ float at(int r, int c) const { return r == 0 ? s[c] : (r == 1 ? p[c].x : p[c].y); }
+};
+__device__ __forceinline__ void m3p_to_array(const M3p& m, float* a) {
+#pragma unroll
+	for(int c = 0; c < 3; ++c) a[3 * c] = m.s[c], a[3 * c + 1] = m.p[c].x, a[3 * c + 2] = m.p[c].y;
+}
+__device__ __forceinline__ M3p m3p_from_array(const float* a) {
+	M3p m;
+#pragma unroll
+	for(int c = 0; c < 3; ++c) m.s[c] = a[3 * c], m.p[c] = mk2(a[3 * c + 1], a[3 * c + 2]);
+	return m;
+}
+// C = A B^T scaled: C[r + 3c] = k * sum_j A[r + 3j] B[c + 3j]
+__device__ __forceinline__ M3p m3p_mul_abt(const M3p& A, const M3p& B, float k) {
+	M3p C;
+#pragma unroll
+	for(int c = 0; c < 3; ++c) {
+		const float b0 = B.at(c, 0) * k, b1 = B.at(c, 1) * k, b2 = B.at(c, 2) * k;
+		C.p[c] = fma2(A.p[2], b2, fma2(A.p[1], b1, mul2(A.p[0], b0)));
+		C.s[c] = fmaf(A.s[2], b2, fmaf(A.s[1], b1, A.s[0] * b0));
+	}
+	return C;
+}
+
+// FIXED_COROTATED without the SVD, packed form of stress_fixed_corotated_polar (same function of F).  Returns false when the
+// Newton iteration did not converge (inverted / nearly singular F): the caller takes the SVD path.
+// Convergence: Newton's polar iteration contracts quadratically, |R_{k+1} - R| ~ |R_{k+1} - R_k|^2 / 2, so a last step of
+// squared Frobenius length < 2e-8 leaves R_{k+1} exact to FP32 rounding (the previous threshold 1e-13 always spent one more
+// iteration to observe that).
+__device__ __forceinline__ bool stress_fixed_corotated_polar_packed(const Mat& m, const M3p& F, M3p& PF) {
+	M3p R = F;
+	float J = 1.f;
+	bool ok = false;
+#pragma unroll 1
+	for(int it = 0; it < 12; ++it) {
+		const float r0 = R.s[0], r1 = R.p[0].x, r2 = R.p[0].y, r3 = R.s[1], r4 = R.p[1].x, r5 = R.p[1].y, r6 = R.s[2], r7 = R.p[2].x, r8 = R.p[2].y;
+		// cofactor matrix (column-major): R^-T = C / det
+		const float c0 = r4 * r8 - r7 * r5, c1 = r6 * r5 - r3 * r8, c2 = r3 * r7 - r6 * r4;
+		const float c3 = r7 * r2 - r1 * r8, c4 = r0 * r8 - r6 * r2, c5 = r6 * r1 - r0 * r7;
+		const float c6 = r1 * r5 - r4 * r2, c7 = r3 * r2 - r0 * r5, c8 = r0 * r4 - r3 * r1;
+		const float det = r0 * c0 + r3 * c3 + r6 * c6;
+		if(it == 0) {
+			J = det;
+			if(det <= 1e-6f) break;
+		}
+		const float h = __fdividef(0.5f, det);
+		M3p N;
+		N.s[0] = fmaf(h, c0, 0.5f * r0);
+		N.s[1] = fmaf(h, c3, 0.5f * r3);
+		N.s[2] = fmaf(h, c6, 0.5f * r6);
+		N.p[0] = fma2(mk2(c1, c2), h, mul2(R.p[0], 0.5f));
+		N.p[1] = fma2(mk2(c4, c5), h, mul2(R.p[1], 0.5f));
+		N.p[2] = fma2(mk2(c7, c8), h, mul2(R.p[2], 0.5f));
+		f2 d2p = mk2(0.f, 0.f);
+		float d2 = 0.f;
+#pragma unroll
+		for(int c = 0; c < 3; ++c) {
+			const f2 d = fma2(R.p[c], -1.f, N.p[c]);
+			d2p = fma2(d, d, d2p);
+			const float e = N.s[c] - R.s[c];
+			d2 = fmaf(e, e, d2);
+		}
+		R = N;
+		if(d2 + d2p.x + d2p.y < 2e-8f) {
+			ok = true;
+			break;
+		}
+	}
+	if(!ok) return false;
+	// P F^T vol = 2 mu vol (F - R) F^T + lambda (J - 1) J vol I
+	M3p D;
+#pragma unroll
+	for(int c = 0; c < 3; ++c) {
+		D.s[c] = F.s[c] - R.s[c];
+		D.p[c] = fma2(R.p[c], -1.f, F.p[c]);
+	}
+	PF = m3p_mul_abt(D, F, 2.f * m.mu * m.volume);
+	const float iso = m.lambda * (J - 1.f) * J * m.volume;
+	PF.s[0] += iso;
+	PF.p[1].x += iso;
+	PF.p[2].y += iso;
+	return true;
 }
 
 // SAND: Drucker-Prager return mapping on the Hencky strain, StVK-Hencky elasticity; F and log_jp are updated

@@ -25,6 +25,24 @@ template<typename T> __host__ __device__ void polar_decomposition(const std::arr
 #include <mgmpm_kernels.cuh>
 #include <particle_buffer.cuh>
 
+// ---- optional: swap single kernels of the reference's loop for libclaymore_b200's (drop-in test) ------------------------------
+// The product library is resolved at run time (dlopen), so this checker has no link-time dependency on it; the calls go through
+// include/claymore_b200_adapter.cuh -- the binding a maintainer of the reference would add -- with the reference's own containers.
+#include <dlfcn.h>
+
+#include <claymore_b200.h>
+#define B200_FUNCS(X)                                                                                                                                                      \
+	X(cb200_g2p2g) X(cb200_update_grid_velocity_query_max) X(cb200_clear_grid) X(cb200_cell_bucket_to_block) X(cb200_compute_bin_capacity) X(cb200_init_adv_bucket)       \
+	X(cb200_register_neighbor_blocks) X(cb200_register_exterior_blocks) X(cb200_mark_active_grid_blocks) X(cb200_mark_active_particle_blocks) X(cb200_exclusive_scan_inverse) \
+	X(cb200_update_partition) X(cb200_update_buckets) X(cb200_copy_selected_grid_blocks) X(cb200_activate_blocks) X(cb200_build_particle_cell_buckets) X(cb200_array_to_buffer) \
+	X(cb200_rasterize) X(cb200_retrieve_particle_buffer)
+#define X(n) static decltype(&::n) g_b200_##n = nullptr;
+B200_FUNCS(X)
+#undef X
+#define CB200_ADAPTER_CALL(name) (*g_b200_##name)
+#include <claymore_b200_adapter.cuh>
+static int g_swap = 0;  // bit 0: g2p2g, bit 1: update_grid_velocity_query_max, bit 2: partition / bucket / grid-carry group, bit 3: init kernels
+
 using namespace mn;
 
 namespace {
@@ -145,17 +163,29 @@ struct Sim : SimBase {
 		float mv = 0.f;
 		for(auto& v : v0s) mv = fmaxf(mv, sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
 		dt = compute_dt(mv, Duration::zero(), Duration(1e30f), Duration(dt_default)).count();
-		for(int m = 0; m < nm; ++m) activate_blocks<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), parts[Rn]);
+		for(int m = 0; m < nm; ++m) {
+			if(g_swap & 8) check_cuda_errors(b200::launch_on(st, {(counts_[m] + 255) / 256, 256}, b200::activate_blocks, (uint32_t) counts_[m], parray(m), parts[Rn]));
+			else activate_blocks<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), parts[Rn]);
+		}
 		fetch(&pbc, parts[Rn].count);
-		for(int m = 0; m < nm; ++m) build_particle_cell_buckets<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), bins[R][m], parts[Rn]);
+		for(int m = 0; m < nm; ++m) {
+			if(g_swap & 8) check_cuda_errors(b200::launch_on(st, {(counts_[m] + 255) / 256, 256}, b200::build_particle_cell_buckets, (uint32_t) counts_[m], parray(m), bins[R][m], parts[Rn]));
+			else build_particle_cell_buckets<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), bins[R][m], parts[Rn]);
+		}
 		for(int m = 0; m < nm; ++m) {
 			PB& pb = bins[R][m];
 			check_cuda_errors(cudaMemsetAsync(pb.particle_bucket_sizes, 0, sizeof(int) * (pbc + 1), st));
-			cell_bucket_to_block<<<pbc, config::G_BLOCKVOLUME, 0, st>>>(pb.cell_particle_counts, pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets);
-			compute_bin_capacity<<<pbc / 128 + 1, 128, 0, st>>>((uint32_t) (pbc + 1), (const int*) pb.particle_bucket_sizes, bin_sizes);
+			if(g_swap & 8) {
+				check_cuda_errors(b200::launch_on(st, {pbc, config::G_BLOCKVOLUME}, b200::cell_bucket_to_block, (const int*) pb.cell_particle_counts, (const int*) pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets));
+				check_cuda_errors(b200::launch_on(st, {pbc / 128 + 1, 128}, b200::compute_bin_capacity, (uint32_t) (pbc + 1), (const int*) pb.particle_bucket_sizes, bin_sizes));
+			} else {
+				cell_bucket_to_block<<<pbc, config::G_BLOCKVOLUME, 0, st>>>(pb.cell_particle_counts, pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets);
+				compute_bin_capacity<<<pbc / 128 + 1, 128, 0, st>>>((uint32_t) (pbc + 1), (const int*) pb.particle_bucket_sizes, bin_sizes);
+			}
 			scan(pbc + 1, bin_sizes, pb.bin_offsets);
 			fetch(&bincount[m], pb.bin_offsets + pbc);
-			array_to_buffer<<<pbc, 128, 0, st>>>(parray(m), pb);
+			if(g_swap & 8) check_cuda_errors(b200::launch_on(st, {pbc, 128}, b200::array_to_buffer, parray(m), pb));
+			else array_to_buffer<<<pbc, 128, 0, st>>>(parray(m), pb);
 		}
 		register_neighbor_blocks<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, parts[Rn]);
 		fetch(&nbc, parts[Rn].count);
@@ -168,8 +198,13 @@ struct Sim : SimBase {
 		check_cuda_errors(cudaStreamSynchronize(st));
 		clear_grid<<<nbc, config::G_BLOCKVOLUME, 0, st>>>(grids[0]);
 		for(int m = 0; m < nm; ++m) {
-			rasterize<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), grids[0], parts[R], Duration(dt), bins[R][m].mass, v0s[m]);
-			init_adv_bucket<<<pbc, 128, 0, st>>>((const int*) bins[Rn][m].particle_bucket_sizes, bins[Rn][m].blockbuckets);
+			if(g_swap & 8) {
+				check_cuda_errors(b200::launch_on(st, {(counts_[m] + 255) / 256, 256}, b200::rasterize, (uint32_t) counts_[m], (const ParticleArray) parray(m), grids[0], (const Partition<1>) parts[R], Duration(dt), bins[R][m].mass, v0s[m]));
+				check_cuda_errors(b200::launch_on(st, {pbc, 128}, b200::init_adv_bucket, (const int*) bins[Rn][m].particle_bucket_sizes, bins[Rn][m].blockbuckets));
+			} else {
+				rasterize<<<(counts_[m] + 255) / 256, 256, 0, st>>>((uint32_t) counts_[m], parray(m), grids[0], parts[R], Duration(dt), bins[R][m].mass, v0s[m]);
+				init_adv_bucket<<<pbc, 128, 0, st>>>((const int*) bins[Rn][m].particle_bucket_sizes, bins[Rn][m].blockbuckets);
+			}
 		}
 		check_cuda_errors(cudaStreamSynchronize(st));
 		return 0;
@@ -180,7 +215,8 @@ struct Sim : SimBase {
 		const int R = rollid, Rn = R ^ 1;
 		const int nm = (int) d_pos.size();
 		check_cuda_errors(cudaMemsetAsync(d_max_vel, 0, sizeof(float), st));
-		update_grid_velocity_query_max<<<(nbc + config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK - 1) / config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK, config::G_NUM_WARPS_PER_CUDA_BLOCK * config::CUDA_WARP_SIZE * config::G_NUM_WARPS_PER_GRID_BLOCK, 0, st>>>((uint32_t) nbc, grids[0], parts[R], Duration(dt), d_max_vel);
+		if(g_swap & 2) check_cuda_errors(b200::launch_on(st, {(nbc + config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK - 1) / config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK, config::G_NUM_WARPS_PER_CUDA_BLOCK * config::CUDA_WARP_SIZE * config::G_NUM_WARPS_PER_GRID_BLOCK}, b200::update_grid_velocity_query_max, (uint32_t) nbc, grids[0], parts[R], Duration(dt), d_max_vel));
+		else update_grid_velocity_query_max<<<(nbc + config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK - 1) / config::G_NUM_GRID_BLOCKS_PER_CUDA_BLOCK, config::G_NUM_WARPS_PER_CUDA_BLOCK * config::CUDA_WARP_SIZE * config::G_NUM_WARPS_PER_GRID_BLOCK, 0, st>>>((uint32_t) nbc, grids[0], parts[R], Duration(dt), d_max_vel);
 		check_cuda_errors(cudaMemcpyAsync(&max_vel, d_max_vel, sizeof(float), cudaMemcpyDefault, st));
 		check_cuda_errors(cudaStreamSynchronize(st));
 		if(std::isinf(max_vel)) return -2;
@@ -189,38 +225,58 @@ struct Sim : SimBase {
 		clear_grid<<<nbc, config::G_BLOCKVOLUME, 0, st>>>(grids[1]);
 		for(int m = 0; m < nm; ++m) {
 			check_cuda_errors(cudaMemsetAsync(bins[Rn][m].cell_particle_counts, 0, sizeof(int) * (size_t) ebc * config::G_BLOCKVOLUME, st));
-			g2p2g<<<pbc, config::G_PARTICLE_BATCH_CAPACITY, 0, st>>>(Duration(dt), Duration(next_dt), (const PB) bins[R][m], bins[Rn][m], (const Partition<1>) parts[Rn], parts[R], (const GridBuffer) grids[0], grids[1]);
+			if(g_swap & 1) check_cuda_errors(b200::launch_on(st, {pbc, config::G_PARTICLE_BATCH_CAPACITY}, b200::g2p2g, Duration(dt), Duration(next_dt), (const PB) bins[R][m], bins[Rn][m], (const Partition<1>) parts[Rn], parts[R], (const GridBuffer) grids[0], grids[1]));
+			else g2p2g<<<pbc, config::G_PARTICLE_BATCH_CAPACITY, 0, st>>>(Duration(dt), Duration(next_dt), (const PB) bins[R][m], bins[Rn][m], (const Partition<1>) parts[Rn], parts[R], (const GridBuffer) grids[0], grids[1]);
 		}
 		check_cuda_errors(cudaStreamSynchronize(st));
 		for(int m = 0; m < nm; ++m) {
 			PB& pb = bins[Rn][m];
 			check_cuda_errors(cudaMemsetAsync(pb.particle_bucket_sizes, 0, sizeof(int) * (ebc + 1), st));
-			cell_bucket_to_block<<<ebc, config::G_BLOCKVOLUME, 0, st>>>(pb.cell_particle_counts, pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets);
+			if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {ebc, config::G_BLOCKVOLUME}, b200::cell_bucket_to_block, (const int*) pb.cell_particle_counts, (const int*) pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets));
+			else cell_bucket_to_block<<<ebc, config::G_BLOCKVOLUME, 0, st>>>(pb.cell_particle_counts, pb.cellbuckets, pb.particle_bucket_sizes, pb.blockbuckets);
 		}
 		check_cuda_errors(cudaMemsetAsync(marks, 0, sizeof(int) * nbc, st));
-		mark_active_grid_blocks<<<(nbc * config::G_BLOCKVOLUME + 127) / 128, 128, 0, st>>>((uint32_t) nbc, (const GridBuffer) grids[1], marks);
+		if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {(nbc * config::G_BLOCKVOLUME + 127) / 128, 128}, b200::mark_active_grid_blocks, (uint32_t) nbc, (const GridBuffer) grids[1], marks));
+		else mark_active_grid_blocks<<<(nbc * config::G_BLOCKVOLUME + 127) / 128, 128, 0, st>>>((uint32_t) nbc, (const GridBuffer) grids[1], marks);
 		check_cuda_errors(cudaMemsetAsync(sources, 0, sizeof(int) * (ebc + 1), st));
-		for(int m = 0; m < nm; ++m) mark_active_particle_blocks<<<ebc / 128 + 1, 128, 0, st>>>((uint32_t) (ebc + 1), (const int*) bins[Rn][m].particle_bucket_sizes, sources);
+		for(int m = 0; m < nm; ++m) {
+			if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {ebc / 128 + 1, 128}, b200::mark_active_particle_blocks, (uint32_t) (ebc + 1), (const int*) bins[Rn][m].particle_bucket_sizes, sources));
+			else mark_active_particle_blocks<<<ebc / 128 + 1, 128, 0, st>>>((uint32_t) (ebc + 1), (const int*) bins[Rn][m].particle_bucket_sizes, sources);
+		}
 		scan(ebc + 1, sources, dest);
 		check_cuda_errors(cudaMemcpyAsync(parts[Rn].count, dest + ebc, sizeof(int), cudaMemcpyDefault, st));
 		check_cuda_errors(cudaMemcpyAsync(&pbc, dest + ebc, sizeof(int), cudaMemcpyDefault, st));
-		exclusive_scan_inverse<<<(ebc + 255) / 256, 256, 0, st>>>(ebc, (const int*) dest, sources);
+		if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {(ebc + 255) / 256, 256}, b200::exclusive_scan_inverse, ebc, (const int*) dest, sources));
+		else exclusive_scan_inverse<<<(ebc + 255) / 256, 256, 0, st>>>(ebc, (const int*) dest, sources);
 		parts[Rn].reset_table(st);
 		check_cuda_errors(cudaStreamSynchronize(st));
-		update_partition<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, (const int*) sources, (const Partition<1>) parts[R], parts[Rn]);
+		if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {(pbc + 127) / 128, 128}, b200::update_partition, (uint32_t) pbc, (const int*) sources, (const Partition<1>) parts[R], parts[Rn]));
+		else update_partition<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, (const int*) sources, (const Partition<1>) parts[R], parts[Rn]);
 		for(int m = 0; m < nm; ++m) {
-			update_buckets<<<pbc, 128, 0, st>>>((uint32_t) pbc, (const int*) sources, (const PB) bins[Rn][m], bins[R][m]);
-			compute_bin_capacity<<<pbc / 128 + 1, 128, 0, st>>>((uint32_t) (pbc + 1), (const int*) bins[R][m].particle_bucket_sizes, bin_sizes);
+			if(g_swap & 4) {
+				check_cuda_errors(b200::launch_on(st, {pbc, 128}, b200::update_buckets, (uint32_t) pbc, (const int*) sources, (const PB) bins[Rn][m], bins[R][m]));
+				check_cuda_errors(b200::launch_on(st, {pbc / 128 + 1, 128}, b200::compute_bin_capacity, (uint32_t) (pbc + 1), (const int*) bins[R][m].particle_bucket_sizes, bin_sizes));
+			} else {
+				update_buckets<<<pbc, 128, 0, st>>>((uint32_t) pbc, (const int*) sources, (const PB) bins[Rn][m], bins[R][m]);
+				compute_bin_capacity<<<pbc / 128 + 1, 128, 0, st>>>((uint32_t) (pbc + 1), (const int*) bins[R][m].particle_bucket_sizes, bin_sizes);
+			}
 			scan(pbc + 1, bin_sizes, bins[R][m].bin_offsets);
 			fetch(&bincount[m], bins[R][m].bin_offsets + pbc);
 		}
-		register_neighbor_blocks<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, parts[Rn]);
+		if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {(pbc + 127) / 128, 128}, b200::register_neighbor_blocks, (uint32_t) pbc, parts[Rn]));
+		else register_neighbor_blocks<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, parts[Rn]);
 		const int prev_nbc = nbc;
 		fetch(&nbc, parts[Rn].count);
-		clear_grid<<<ebc, config::G_BLOCKVOLUME, 0, st>>>(grids[0]);
-		copy_selected_grid_blocks<<<prev_nbc, config::G_BLOCKVOLUME, 0, st>>>((const ivec3*) parts[R].active_keys, (const Partition<1>) parts[Rn], (const int*) marks, grids[1], grids[0]);
+		if(g_swap & 4) {
+			check_cuda_errors(b200::launch_on(st, {ebc, config::G_BLOCKVOLUME}, b200::clear_grid, grids[0]));
+			check_cuda_errors(b200::launch_on(st, {prev_nbc, config::G_BLOCKVOLUME}, b200::copy_selected_grid_blocks, (const ivec3*) parts[R].active_keys, (const Partition<1>) parts[Rn], (const int*) marks, grids[1], grids[0]));
+		} else {
+			clear_grid<<<ebc, config::G_BLOCKVOLUME, 0, st>>>(grids[0]);
+			copy_selected_grid_blocks<<<prev_nbc, config::G_BLOCKVOLUME, 0, st>>>((const ivec3*) parts[R].active_keys, (const Partition<1>) parts[Rn], (const int*) marks, grids[1], grids[0]);
+		}
 		check_cuda_errors(cudaStreamSynchronize(st));
-		register_exterior_blocks<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, parts[Rn]);
+		if(g_swap & 4) check_cuda_errors(b200::launch_on(st, {(pbc + 127) / 128, 128}, b200::register_exterior_blocks, (uint32_t) pbc, parts[Rn]));
+		else register_exterior_blocks<<<(pbc + 127) / 128, 128, 0, st>>>((uint32_t) pbc, parts[Rn]);
 		fetch(&ebc, parts[Rn].count);
 		if(ebc > (int) config::G_MAX_ACTIVE_BLOCK) return -1;
 		rollid = Rn;
@@ -270,6 +326,22 @@ struct Sim : SimBase {
 extern "C" {
 #define REF_API __attribute__((visibility("default")))
 REF_API int refgpu_domain_bits() { return config::DOMAIN_BITS; }
+// route the kernels selected by `mask` (see g_swap) through libclaymore_b200 (path of the .so); mask 0 restores the reference's own
+REF_API int refgpu_swap(const char* libpath, int mask) {
+	if(mask == 0) {
+		g_swap = 0;
+		return 0;
+	}
+	void* h = dlopen(libpath, RTLD_NOW | RTLD_GLOBAL);
+	if(!h) return -1;
+#define X(n)                                       \
+	g_b200_##n = (decltype(&::n)) dlsym(h, #n); \
+	if(!g_b200_##n) return -2;
+	B200_FUNCS(X)
+#undef X
+	g_swap = mask;
+	return 0;
+}
 REF_API int refgpu_max_blocks() { return (int) config::G_MAX_ACTIVE_BLOCK; }
 REF_API void* refgpu_create(int material, float dt_default) {
 	switch(material) {

@@ -35,11 +35,22 @@ class RefGpuSim:
         L.refgpu_dt.restype = C.c_float
         L.refgpu_dt.argtypes = [C.c_void_p]
         L.refgpu_destroy.argtypes = [C.c_void_p]
+        if hasattr(L, "refgpu_swap"):
+            L.refgpu_swap.argtypes = [C.c_char_p, C.c_int]
         assert L.refgpu_domain_bits() == bits
         self.max_blocks = L.refgpu_max_blocks()
         self.material = material
         self.h = L.refgpu_create(material, dt_default)
         self.counts = []
+
+    def swap(self, mask, libpath=None):
+        """Route the reference kernels selected by `mask` through libclaymore_b200 via include/claymore_b200_adapter.cuh
+        (bit 0 g2p2g, 1 update_grid_velocity_query_max, 2 partition / bucket / grid-carry group, 3 init kernels); 0 = all reference."""
+        if libpath is None:
+            import claymore_b200 as cb
+            libpath = cb.lib_path()
+        rc = self.L.refgpu_swap(libpath.encode(), mask)
+        assert rc == 0, f"refgpu_swap failed: {rc}"
 
     def init_model(self, pos, v0, params):
         pos = np.ascontiguousarray(pos, np.float32)
@@ -96,10 +107,11 @@ def material_params(material, dx):
     return [1e3, vol, 5e3, 0.4]
 
 
-def build_ref(scene, dt=1e-4):
+def build_ref(scene, dt=1e-4, swap_mask=0):
     bits = scene["domain_bits"]
     material = scene["models"][0]["material"]
     sim = RefGpuSim(bits, material, dt)
+    sim.swap(swap_mask) if (swap_mask or hasattr(sim.L, "refgpu_swap")) else None
     dx = 1.0 / (1 << bits)
     for m in scene["models"]:
         assert m["material"] == material

@@ -83,3 +83,74 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_capi, "_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(_capi.CB200Error):
         _capi.lib()
+
+
+def test_adapter_header_compiles_against_the_reference(tmp_path):
+    """include/claymore_b200_adapter.cuh -- the C++ overloads with the reference's kernel argument lists -- must compile against the
+    reference's own headers with every functor instantiated for every material (only where /root/reference exists)."""
+    import shutil
+    import subprocess
+    ref = os.environ.get("CLAYMORE_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref) or not shutil.which("nvcc") and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("reference checkout or nvcc not available")
+    tu = tmp_path / "adapter_tu.cu"
+    tu.write_text(r"""
+#include <MnBase/Math/Matrix/Givens.cuh>
+namespace mn { namespace math { template<typename T> __host__ __device__ void polar_decomposition(const std::array<T, 4>& a, GivensRotation<T>& r, std::array<T, 4>& s); }}
+#include <claymore_b200_adapter.cuh>
+using namespace mn;
+struct Ctx { cudaStream_t stream_compute() { return nullptr; } };
+template<MaterialE M> void every_call(Ctx& cu, ParticleBuffer<M>& pb, ParticleBuffer<M>& next, Partition<1>& part, Partition<1>& prev, GridBuffer& g0, GridBuffer& g1, ParticleArray& pa, int* marks, float* mv) {
+    b200::compute_launch(cu, {8, 128}, b200::g2p2g, Duration(1e-4f), Duration(1e-4f), (const ParticleBuffer<M>) pb, next, (const Partition<1>) prev, part, (const GridBuffer) g0, g1);
+    b200::compute_launch(cu, {8, 128}, b200::update_buckets, (uint32_t) 8, (const int*) marks, (const ParticleBuffer<M>) pb, next);
+    b200::compute_launch(cu, {8, 128}, b200::build_particle_cell_buckets, (uint32_t) 8, pa, pb, part);
+    b200::compute_launch(cu, {8, 128}, b200::array_to_buffer, pa, pb);
+    b200::compute_launch(cu, {8, 128}, b200::retrieve_particle_buffer, part, prev, pb, next, pa, marks);
+    (void) mv;
+}
+void common_calls(Ctx& cu, Partition<1>& part, Partition<1>& prev, GridBuffer& g0, GridBuffer& g1, ParticleArray& pa, int* marks, float* mv) {
+    b200::compute_launch(cu, {8, 128}, b200::update_grid_velocity_query_max, (uint32_t) 8, g0, part, Duration(1e-4f), mv);
+    b200::compute_launch(cu, {8, 64}, b200::clear_grid, g1);
+    b200::compute_launch(cu, {8, 64}, b200::cell_bucket_to_block, (const int*) marks, (const int*) marks, marks, marks);
+    b200::compute_launch(cu, {8, 128}, b200::compute_bin_capacity, (uint32_t) 8, (const int*) marks, marks);
+    b200::compute_launch(cu, {8, 128}, b200::init_adv_bucket, (const int*) marks, marks);
+    b200::compute_launch(cu, {8, 128}, b200::register_neighbor_blocks, (uint32_t) 8, part);
+    b200::compute_launch(cu, {8, 128}, b200::register_exterior_blocks, (uint32_t) 8, part);
+    b200::compute_launch(cu, {8, 128}, b200::mark_active_grid_blocks, (uint32_t) 8, (const GridBuffer) g1, marks);
+    b200::compute_launch(cu, {8, 128}, b200::mark_active_particle_blocks, (uint32_t) 8, (const int*) marks, marks);
+    b200::compute_launch(cu, {8, 128}, b200::exclusive_scan_inverse, 8, (const int*) marks, marks);
+    b200::compute_launch(cu, {8, 128}, b200::update_partition, (uint32_t) 8, (const int*) marks, (const Partition<1>) prev, part);
+    b200::compute_launch(cu, {8, 64}, b200::copy_selected_grid_blocks, (const ivec3*) part.active_keys, (const Partition<1>) part, (const int*) marks, g1, g0);
+    b200::compute_launch(cu, {8, 128}, b200::activate_blocks, (uint32_t) 8, pa, part);
+    b200::compute_launch(cu, {8, 128}, b200::rasterize, (uint32_t) 8, (const ParticleArray) pa, g0, (const Partition<1>) part, Duration(1e-4f), 1.f, std::array<float, 3> {0.f, 0.f, 0.f});
+}
+template void every_call<MaterialE::J_FLUID>(Ctx&, ParticleBuffer<MaterialE::J_FLUID>&, ParticleBuffer<MaterialE::J_FLUID>&, Partition<1>&, Partition<1>&, GridBuffer&, GridBuffer&, ParticleArray&, int*, float*);
+template void every_call<MaterialE::FIXED_COROTATED>(Ctx&, ParticleBuffer<MaterialE::FIXED_COROTATED>&, ParticleBuffer<MaterialE::FIXED_COROTATED>&, Partition<1>&, Partition<1>&, GridBuffer&, GridBuffer&, ParticleArray&, int*, float*);
+template void every_call<MaterialE::SAND>(Ctx&, ParticleBuffer<MaterialE::SAND>&, ParticleBuffer<MaterialE::SAND>&, Partition<1>&, Partition<1>&, GridBuffer&, GridBuffer&, ParticleArray&, int*, float*);
+template void every_call<MaterialE::NACC>(Ctx&, ParticleBuffer<MaterialE::NACC>&, ParticleBuffer<MaterialE::NACC>&, Partition<1>&, Partition<1>&, GridBuffer&, GridBuffer&, ParticleArray&, int*, float*);
+""")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    inc = [f"-I{ref}/Library", f"-I{ref}/Projects/GMPM", f"-I{ref}/Externals/function_ref", f"-I{ref}/Externals/optional", f"-I{ref}/Externals/variant", f"-I{ROOT}/include"]
+    cmd = [nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-extended-lambda", "--expt-relaxed-constexpr", "-DQR_CUH", "-include", "chrono",
+           *inc, "-c", "-o", str(tmp_path / "adapter_tu.o"), str(tu)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-6000:]
+
+
+def test_cmake_build_exports_the_same_abi(tmp_path):
+    """CMakeLists.txt (sm_100a pinned) builds the same library for CMake consumers such as the reference tree."""
+    import shutil
+    import subprocess
+    cmake = shutil.which("cmake")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not cmake or not os.path.exists(nvcc):
+        pytest.skip("cmake / nvcc not available")
+    b = str(tmp_path / "build")
+    r = subprocess.run([cmake, "-S", ROOT, "-B", b, f"-DCMAKE_CUDA_COMPILER={nvcc}"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "100a" in open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    r = subprocess.run([cmake, "--build", b, "-j", "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    lib = C.CDLL(os.path.join(b, "libclaymore_b200.so"))
+    missing = [n for n in _declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing

@@ -194,3 +194,34 @@ def test_reference_loop_through_kernel_level_abi(oracle, cuda_lib, case):
             assert len(so) == len(sd)
             scenes.match_particles(so, sd, tol=5e-6)
         assert abs(dsim.dt - osim.dt) <= 1e-9
+
+
+# ---- the reference's own host loop and containers with single kernels swapped for the library's --------------------------------
+@pytest.mark.parametrize("material", [scenes.FIXED_COROTATED, scenes.J_FLUID, scenes.SAND])
+@pytest.mark.parametrize("mask,what", [(1, "g2p2g"), (2, "update_grid_velocity_query_max"), (4, "partition / bucket / carry group"), (8, "init kernels"), (15, "everything")])
+def test_reference_loop_with_swapped_kernels(cuda_lib, material, mask, what):
+    """oracle/ref_gpu_driver.cu drives the reference's REAL ParticleBuffer<M> / Partition<1> / GridBuffer instances through the
+    reference's launch sequence (gmpm_simulator.cuh:324-580, 637-781); refgpu_swap routes the selected kernels through
+    include/claymore_b200_adapter.cuh -> the C ABI.  The swapped run must reproduce the all-reference run: block counts and key
+    sets per class bit-exact, per-cell mass 2e-5, momentum 2e-4 of the max, particle states matched by position."""
+    import ref_gpu_binding as rg
+    from test_oracle_cpu import compare_with_ref_gpu_golden
+    if not rg.available(6):
+        pytest.skip("oracle/_ref/libclaymore_ref_gpu_d6.so not built")
+    if mask not in (1, 15) and material != scenes.FIXED_COROTATED:
+        pytest.skip("material independent kernels: covered once")
+    scene = scenes.small_cube(material=material, jitter_seed=5)
+    ref = rg.build_ref(scene, swap_mask=0)
+    ref.step(12)
+    pbc, nbc, ebc = ref.block_counts()
+    keys = ref.active_keys()
+    h = scenes.key_hash(keys)
+    gh, gg = scenes.grid_by_key(keys, ref.grid())
+    golden = {"s12_counts": np.array([pbc, nbc, ebc]), "s12_keys_particle": np.sort(h[:pbc]), "s12_keys_neighbor": np.sort(h[pbc:nbc]),
+              "s12_keys_exterior": np.sort(h[nbc:ebc]), "s12_grid_keys": gh, "s12_grid": gg, "s12_state0": ref.particle_state(0)}
+    ref.close()
+    swapped = rg.build_ref(scene, swap_mask=mask)
+    swapped.step(12)
+    compare_with_ref_gpu_golden(swapped, golden, 12, 1, f"reference loop with {what} swapped")
+    swapped.close()
+    rg.RefGpuSim(6, material).swap(0)   # leave the shared library in its all-reference state

@@ -35,7 +35,7 @@ def _torch():
 # ---------------------------------------------------------------------------------------------------------------------------
 # engine vs live reference kernels at benchmark scale
 # ---------------------------------------------------------------------------------------------------------------------------
-def _compare_with_live_reference(ref, esim, nmodels, label, sample=200_000, pos_tol=5e-6, f_tol=5e-4, mass_tol=2e-5):
+def _compare_with_live_reference(ref, esim, nmodels, label, sample=200_000, pos_tol=5e-6, f_tol=5e-4, mass_tol=2e-5, mom_tol=2e-4):
     st = esim.stats()
     assert st.error == 0, (label, st.error)
     pbc, nbc, ebc = ref.block_counts()
@@ -50,7 +50,7 @@ def _compare_with_live_reference(ref, esim, nmodels, label, sample=200_000, pos_
     mscale = float(mass_r.max())
     assert np.abs(mass_e - mass_r).max() <= mass_tol * mscale, f"{label}: cell mass {np.abs(mass_e - mass_r).max() / mscale:.3e} of max"
     pscale = float(np.abs(rg[:, 1:]).max())
-    assert np.abs(eg[:, 1:] - rg[:, 1:]).max() <= 2e-4 * pscale, f"{label}: cell momentum {np.abs(eg[:, 1:] - rg[:, 1:]).max() / pscale:.3e} of max"
+    assert np.abs(eg[:, 1:] - rg[:, 1:]).max() <= mom_tol * pscale, f"{label}: cell momentum {np.abs(eg[:, 1:] - rg[:, 1:]).max() / pscale:.3e} of max"
     tm_r, tm_e = mass_r.sum(dtype=np.float64), mass_e.sum(dtype=np.float64)
     assert abs(tm_e - tm_r) <= 1e-6 * tm_r, label
     tp_r, tp_e = rg[:, 1:].sum(axis=(0, 2), dtype=np.float64), eg[:, 1:].sum(axis=(0, 2), dtype=np.float64)
@@ -89,26 +89,36 @@ def test_config2_5m_vs_live_reference(cuda_lib):
     esim.close()
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(1200)
 @pytest.mark.parametrize("name", ["sand2m_512", "fluid1m_512"])
-def test_sand_and_fluid_1m_vs_live_reference(cuda_lib, name):
+def test_sand_and_fluid_1m_vs_live_reference_and_oracle(oracle, cuda_lib, name):
+    """>= 1 M particles on the 512^3 grid, 20 sub-steps, three-way: the engine against the LIVE reference kernels and against the
+    oracle (the exact-arithmetic restatement, pinned bitwise to the reference's math).
+    Engine vs oracle: per-cell mass 2e-5, momentum 2e-4 of the max.  Engine vs live reference: the reference build uses
+    --use_fast_math; for sand at rest the Hencky strains are ~1e-6, where its approximate logf is off by ~10 %, so its stress --
+    and after 20 sub-steps ~2e-3 of the (tiny) cell momentum -- is noise; measured 2.1e-3, bound 5e-3 (sand) / 2e-4 (fluid)."""
     import ref_gpu_binding as rg
     if not rg.available(9):
         pytest.skip("oracle/_ref/libclaymore_ref_gpu_d9.so not built")
-    scene = scenes.sand_column(domain_bits=9, size=(50, 100, 50)) if name.startswith("sand") else scenes.fluid_dam(domain_bits=9, size=(64, 40, 64), base=(12, 12, 12))
+    sand = name.startswith("sand")
+    scene = scenes.sand_column(domain_bits=9, size=(50, 100, 50)) if sand else scenes.fluid_dam(domain_bits=9, size=(64, 40, 64), base=(12, 12, 12))
     assert scenes.n_particles(scene) >= 1_000_000
+    mb = scenes.max_blocks_for(scene, 4.0)
     ref = rg.build_ref(scene)
-    esim = scenes.build_engine(scene, max_blocks=scenes.max_blocks_for(scene, 4.0))
+    esim = scenes.build_engine(scene, max_blocks=mb)
+    osim = scenes.build_oracle(oracle, scene, max_blocks=mb, threads=min(os.cpu_count() or 1, 32))
     done = 0
     for cp in (1, 20):
         ref.step(cp - done)
         esim.step(cp - done)
+        osim.step(cp - done)
         done = cp
-        # after 20 sub-steps of plastic flow the fast-math reference and the engine differ by ~1e-6 dx in particle positions:
-        # per-cell mass 5e-5 of the max (measured 2.3e-5), momentum 2e-4 of the max
-        _compare_with_live_reference(ref, esim, 1, f"{name} step {cp}", f_tol=1e-3, mass_tol=2e-5 if cp == 1 else 5e-5)
+        _compare_with_live_reference(ref, esim, 1, f"{name} step {cp} vs live reference", f_tol=1e-3, mass_tol=2e-5 if cp == 1 else 5e-5,
+                                     mom_tol=2e-4 if (cp == 1 or not sand) else 5e-3)
+        _compare_with_live_reference(osim, esim, 1, f"{name} step {cp} vs oracle", f_tol=2e-4, mass_tol=2e-5, mom_tol=2e-4)
     ref.close()
     esim.close()
+    osim.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
