@@ -163,8 +163,9 @@ def lib():
             fn.restype = C.c_int
         L.cb200_sim_launch_count.argtypes = [_P]
         L.cb200_sim_launch_count.restype = C.c_longlong
-        L.cb200_default_material.argtypes = [_CFG, _I, C.POINTER(ParticleBuffer)]
-        L.cb200_default_material.restype = None
+        if hasattr(L, "cb200_default_material"):
+            L.cb200_default_material.argtypes = [_CFG, _I, C.POINTER(ParticleBuffer)]
+            L.cb200_default_material.restype = None
         L.cb200_version.restype = C.c_char_p
         L.cb200_error_string.restype = C.c_char_p
         L.cb200_error_string.argtypes = [_I]

@@ -25,6 +25,56 @@
 #include "partition.cuh"
 
 namespace cb200 {
+// mark_overlapping_blocks for every peer (mgsp_tag_kernel) with the end-of-step bookkeeping in its last CTA: global max |v|^2,
+// the halo epoch of this sub-step, the roll of the device-resident step state (finalize_step) and the reset of this rank's
+// local maximum for the next carry.  One launch instead of tag + halo statistics + finalize.
+__global__ void __launch_bounds__(256) mgsp_tag_finalize_kernel(Cfg cfg, MgspView v, const int* table, int* overlap_marks, const int* key_limit, float* local_max_vel, float* global_max_vel, FinalizeArgs fin) {
+	const int limit = *key_limit;
+	float gmax = *local_max_vel;
+	const int epoch = v.epochs[2] + 1, par = epoch & 1;
+	for(int p = 0; p < v.world; ++p) {
+		if(p == v.rank) continue;
+		unsigned char* seg = seg_of(v, v.rank, par, p);
+		InboxHeader* hd = reinterpret_cast<InboxHeader*>(seg);
+		if(threadIdx.x == 0) wait_flag(&hd->flag_keys, epoch);
+		__syncthreads();
+		const int n = *reinterpret_cast<volatile int*>(&hd->key_count);
+		gmax = fmaxf(gmax, *reinterpret_cast<volatile float*>(&hd->max_vel_sq));
+		const int* rk = reinterpret_cast<const int*>(seg + v.L.off_keys);
+		int* outk = v.overlap_keys + (size_t) p * v.L.max_blocks * 3;
+		for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+			const int x = rk[3 * i], y = rk[3 * i + 1], z = rk[3 * i + 2];
+			const int bno = table_query(cfg, table, x, y, z);
+			if(bno >= 0 && bno < limit) {
+				atomicOr(overlap_marks + bno, 1 << p);
+				v.peer_bno[(size_t) p * v.L.max_blocks + bno] = i;  // the peer's keys arrive in its block order
+				const int h = atomicAdd(&v.overlap_count[p], 1);
+				if(h < v.L.max_blocks) {
+					outk[3 * h] = x;
+					outk[3 * h + 1] = y;
+					outk[3 * h + 2] = z;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	__shared__ int s_last;
+	if(threadIdx.x == 0) {
+		__threadfence();
+		s_last = atomicAdd(&v.done[3], 1) == (int) gridDim.x - 1;
+	}
+	__syncthreads();
+	if(s_last && threadIdx.x == 0) {
+		__threadfence();
+		v.done[3] = 0;
+		v.epochs[2] = epoch;
+		v.epochs[1] = v.epochs[1] + 1;  // the halo ("my reductions have landed") epoch of this sub-step: published behind g2p2g, awaited by the carry
+		*global_max_vel = gmax;         // every CTA saw every header; the last one publishes
+		finalize_step(fin);             // reads *global_max_vel through fin.next_max_vel
+		*local_max_vel = 0.f;           // for the next sub-step's carry
+	}
+}
+
 int num_sms();
 cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaStream_t s);
 void g2p2g_prepare_all();
@@ -405,6 +455,7 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 	return (int) cudaGetLastError();
 }
 int mark_phase(cb200_sim* s, int id);
+MgspView mgsp_view(cb200_sim* s);
 int enqueue_halo_publish(cb200_sim* s, int P, const float* local_max);
 int enqueue_halo_tag_reset(cb200_sim* s, int P);
 int enqueue_halo_tag(cb200_sim* s, int P, const int* particle_block_count, const float* local_max, float* global_max);
@@ -421,12 +472,17 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 	const bool mgsp = s->desc.mgsp_world > 1;
 	float* local_max = reinterpret_cast<float*>(s->d_scratch + 3);
 	float* global_max = reinterpret_cast<float*>(s->d_scratch + 4);
-	if(mgsp) {
-		CK(cudaMemsetAsync(local_max, 0, sizeof(float), st));
-		CK(enqueue_halo_tag_reset(s, Rn));
-	}
 	{
 		CarryArgs a {};
+		if(mgsp) {  // behind the wait for the peers' "reductions landed" flags; resets the tagging state of the new partition on the way
+			mgsp_done_wait_kernel<<<1, 32, 0, st>>>(mgsp_view(s));
+			++s->launches;
+			a.mgsp = 1;
+			a.view = mgsp_view(s);
+			a.overlap_marks = s->part[Rn].overlap_marks;
+			a.halo_count = s->part[Rn].halo_count;
+			a.interior_count = s->interior_count[Rn];
+		}
 		a.cfg = s->cfg;
 		a.new_count = s->d_scratch + 1;
 		a.new_keys = s->part[Rn].active_keys;
@@ -439,9 +495,8 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 		++s->launches;
 	}
 	if(mgsp) {
-		clear_grid_dev_kernel<<<grid_blocks(4), 256, 0, st>>>(s->d_scratch + 1, s->grid[1]);
+		mgsp_clear_publish_kernel<<<grid_blocks(2), 256, 0, st>>>(mgsp_view(s), s->part[Rn].active_keys, s->d_scratch + 1, local_max, s->grid[1]);
 		++s->launches;
-		CK(enqueue_halo_publish(s, Rn, local_max));
 	}
 	FinalizeArgs fin {};
 	fin.cfg = s->cfg;
@@ -474,10 +529,9 @@ int enqueue_carry_and_exterior(cb200_sim* s, int R) {
 	}
 	if(mgsp) {
 		mark_phase(s, 9);
-		CK(enqueue_halo_tag(s, Rn, s->d_scratch + 0, local_max, global_max));
-		mark_phase(s, 8);
-		finalize_step_kernel<<<1, 32, 0, st>>>(fin);
+		mgsp_tag_finalize_kernel<<<grid_blocks(1), 256, 0, st>>>(s->cfg, mgsp_view(s), s->part[Rn].index_table, s->part[Rn].overlap_marks, s->d_scratch + 1, local_max, global_max, fin);
 		++s->launches;
+		mark_phase(s, 8);
 	}
 	return (int) cudaGetLastError();
 }
@@ -558,7 +612,7 @@ int enqueue_substep(cb200_sim* s, int R) {
 		// reduction has landed".
 		if((e = enqueue_g2p2g(s, R, 0))) return e;
 		mark_phase(s, 5);
-		mgsp_done_barrier_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s));
+		mgsp_done_publish_kernel<<<1, 32, 0, s->stream>>>(mgsp_view(s));  // the wait sits at the head of the grid carry
 		++s->launches;
 		mark_phase(s, 6);
 		if((e = enqueue_rebuild(s, R))) return e;
@@ -619,6 +673,10 @@ void preload_kernels() {
 	preload(mgsp_tag_reset_kernel);
 	preload(mgsp_tag_kernel);
 	preload(mgsp_done_barrier_kernel);
+	preload(mgsp_done_publish_kernel);
+	preload(mgsp_done_wait_kernel);
+	preload(mgsp_clear_publish_kernel);
+	preload(mgsp_tag_finalize_kernel);
 	preload(clear_grid_dev_kernel);
 	preload(grid_max_kernel);
 	g2p2g_prepare_all();
@@ -1228,28 +1286,48 @@ int cb200_sim_mgsp_inbox(cb200_sim* s, void** inbox, void** next_grid, size_t* i
 	if(inbox_bytes_out) *inbox_bytes_out = inbox_bytes(s->inbox_layout);
 	return 0;
 }
-// 128 bytes: cudaIpcMemHandle_t of the inbox, then of the next-grid buffer (target of the peers' fused halo reductions)
-int cb200_sim_mgsp_ipc_handle(cb200_sim* s, void* handle128) {
-	if(!s || s->desc.mgsp_world <= 1 || !handle128) return (int) cudaErrorInvalidValue;
-	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+// CB200_MGSP_HANDLE_BYTES (160) bytes: cudaIpcMemHandle_t of the inbox, then of the next-grid buffer (target of the peers' fused halo
+// reductions), then the parameters every rank must agree on -- the inbox layout is computed from them on BOTH sides of a
+// transfer: {max_blocks, halo_cap, world, domain_bits, max_ppc}
+static void mgsp_layout_words(const cb200_sim* s, int* w) {
+	w[0] = s->desc.max_blocks;
+	w[1] = s->desc.mgsp_halo_cap;
+	w[2] = s->desc.mgsp_world;
+	w[3] = s->desc.cfg.domain_bits;
+	w[4] = s->desc.cfg.max_ppc;
+	w[5] = w[6] = w[7] = 0;
+}
+int cb200_sim_mgsp_ipc_handle(cb200_sim* s, void* handle) {
+	if(!s || s->desc.mgsp_world <= 1 || !handle) return (int) cudaErrorInvalidValue;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64 && CB200_MGSP_HANDLE_BYTES == 160, "IPC handle blob layout");
 	cudaIpcMemHandle_t h;
 	CK(cudaIpcGetMemHandle(&h, s->inbox_local));
-	memcpy(handle128, &h, 64);
+	memcpy(handle, &h, 64);
 	CK(cudaIpcGetMemHandle(&h, s->grid[1]));
-	memcpy((unsigned char*) handle128 + 64, &h, 64);
+	memcpy((unsigned char*) handle + 64, &h, 64);
+	int w[8];
+	mgsp_layout_words(s, w);
+	memcpy((unsigned char*) handle + 128, w, 32);
 	return 0;
 }
 int cb200_sim_mgsp_open_peers(cb200_sim* s, const void* handles) {
 	if(!s || s->desc.mgsp_world <= 1 || !handles) return (int) cudaErrorInvalidValue;
+	int mine[8];
+	mgsp_layout_words(s, mine);
+	for(int r = 0; r < s->desc.mgsp_world; ++r) {  // a rank with another block capacity would lay out its messages differently
+		int theirs[8];
+		memcpy(theirs, (const unsigned char*) handles + CB200_MGSP_HANDLE_BYTES * r + 128, 32);
+		if(memcmp(mine, theirs, 32) != 0) return (int) cudaErrorInvalidValue;
+	}
 	for(int r = 0; r < s->desc.mgsp_world; ++r) {
 		if(r == s->desc.mgsp_rank) continue;
 		cudaIpcMemHandle_t h;
 		void* p = nullptr;
-		memcpy(&h, (const unsigned char*) handles + 128 * r, 64);
+		memcpy(&h, (const unsigned char*) handles + CB200_MGSP_HANDLE_BYTES * r, 64);
 		CK(g_ipc.open(&p, h));
 		s->inbox_peer[r] = (unsigned char*) p;
 		s->inbox_opened[r] = true;
-		memcpy(&h, (const unsigned char*) handles + 128 * r + 64, 64);
+		memcpy(&h, (const unsigned char*) handles + CB200_MGSP_HANDLE_BYTES * r + 64, 64);
 		CK(g_ipc.open(&p, h));
 		s->grid1_peer[r] = (float*) p;
 		s->grid1_opened[r] = true;
@@ -1269,6 +1347,13 @@ int cb200_sim_mgsp_set_peers(cb200_sim* s, void* const* inbox_ptrs, void* const*
 }
 int cb200_sim_mgsp_halo_counts(cb200_sim* s, int* shared, int* halo_particle_blocks) {
 	if(!s || s->desc.mgsp_world <= 1) return (int) cudaErrorInvalidValue;
+	if(s->setup_done) {  // the halo / interior particle-block lists are statistics only in the fused path: built on demand, not per sub-step
+		const int P = s->rollid;
+		CK(cudaMemsetAsync(s->part[P].halo_count, 0, sizeof(int), s->stream));
+		CK(cudaMemsetAsync(s->interior_count[P], 0, sizeof(int), s->stream));
+		collect_halo_blockids_kernel<<<grid_blocks(2), 128, 0, s->stream>>>(s->cfg, count_dev(&s->d_state->pbc), s->part[P].index_table, s->part[P].active_keys, s->part[P].overlap_marks, s->part[P].halo_marks, s->part[P].halo_count, nullptr, s->halo_list[P], s->interior_list[P], s->interior_count[P]);
+		++s->launches;
+	}
 	CK(cudaStreamSynchronize(s->stream));
 	if(shared) CK(cudaMemcpy(shared, s->peer_overlap_count, s->desc.mgsp_world * sizeof(int), cudaMemcpyDeviceToHost));
 	if(halo_particle_blocks) CK(cudaMemcpy(halo_particle_blocks, s->part[s->rollid].halo_count, sizeof(int), cudaMemcpyDeviceToHost));

@@ -1,6 +1,7 @@
 // grid.cuh -- sparse-grid block kernels: velocity update + max query (+ fused clears), carry copy.
 #pragma once
 #include "common.cuh"
+#include "mgsp.cuh"
 
 namespace cb200 {
 
@@ -114,18 +115,38 @@ struct CarryArgs {
 	float* new_grid;
 	float* next_max_vel;    // nullable (MGSP): max |v|^2 the NEXT grid update will find on this rank, so that the all-reduce
 	                        // of it can ride on the end-of-step key exchange instead of being a sync point of its own
+	// MGSP: reset the tagging state of the new partition on the way (reset_overlap_marks / reset_halo_count, hash_table.cuh:60-66);
+	// the launch sits behind mgsp_done_wait_kernel: the old next-grid is complete only when every peer's halo reductions have landed
+	int mgsp;
+	MgspView view;
+	int* overlap_marks;
+	int* halo_count;
+	int* interior_count;
 };
 __global__ void __launch_bounds__(256) carry_grid_kernel(const CarryArgs a) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = *a.new_count;
 	const int old_nbc = a.state->nbc;
 	const int g = a.cfg.gsize, bc = a.cfg.boundary;
+	if(a.mgsp) {
+		if(blockIdx.x == 0) {
+			if((int) threadIdx.x < a.view.world) a.view.overlap_count[threadIdx.x] = 0;
+			if(threadIdx.x == 0) {
+				*a.halo_count = 0;
+				*a.interior_count = 0;
+			}
+		}
+	}
 	float gdt = 0.f;
 	if(a.next_max_vel) gdt = a.cfg.gravity * device_compute_dt(a.cfg, a.state->max_vel_sq, a.state->step_time, a.state->frame_time, a.state->dt_default);
 	unsigned vmax = 0u;
 	for(int j = blockIdx.x * 8 + warp; j < n; j += gridDim.x * 8) {
 		const int kx = a.new_keys[3 * j], ky = a.new_keys[3 * j + 1], kz = a.new_keys[3 * j + 2];
 		const int src = table_query(a.cfg, a.old_table, kx, ky, kz);
+		if(a.mgsp) {
+			if(lane == 0) a.overlap_marks[j] = 0;
+			if(lane < a.view.world) a.view.peer_bno[(size_t) lane * a.view.L.max_blocks + j] = -1;
+		}
 		float4* d = reinterpret_cast<float4*>(a.new_grid + (size_t) j * kGridBlockFloats);
 		if(src >= 0 && src < old_nbc) {
 			const float4* s = reinterpret_cast<const float4*>(a.old_grid + (size_t) src * kGridBlockFloats);

@@ -120,6 +120,25 @@ __global__ void mgsp_done_barrier_kernel(MgspView v) {
 	if(t == 0) v.epochs[1] = epoch;
 }
 
+// The two halves of that barrier as used by the step driver: the flag is published right behind g2p2g, the wait sits at the head
+// of the first kernel that reads the reduced grid (the grid carry), behind the partition rebuild -- a rank that finishes its g2p2g
+// late costs its peers nothing as long as it is less late than their rebuild takes.  epochs[1] is advanced by the tag kernel.
+__global__ void mgsp_done_publish_kernel(MgspView v) {
+	const int epoch = v.epochs[1] + 1, par = epoch & 1;
+	const int t = threadIdx.x;
+	if(t < v.world && t != v.rank) {
+		InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, t, par, v.rank));
+		__threadfence_system();
+		st_release_sys(&h->flag_halo, epoch);
+	}
+}
+// one warp: a wide kernel spinning on the flags would hold the SMs of ranks that share a GPU (tests) hostage
+__global__ void mgsp_done_wait_kernel(MgspView v) {
+	const int epoch = v.epochs[1] + 1, par = epoch & 1;
+	const int t = threadIdx.x;
+	if(t < v.world && t != v.rank) wait_flag(&reinterpret_cast<InboxHeader*>(seg_of(v, v.rank, par, t))->flag_halo, epoch);
+}
+
 // ---- halo pack + send (collect_grid_blocks + HaloGridBlocks::send, halo_kernels.cuh:65-80, halo_buffer.cuh:54-59) ---
 // warp per block: reads my next-grid block, stores it (and its key) into the peer's inbox over NVLink
 __global__ void __launch_bounds__(256) mgsp_pack_send_kernel(Cfg cfg, MgspView v, const float* grid, const int* table) {
@@ -229,6 +248,41 @@ __global__ void __launch_bounds__(256) mgsp_publish_keys_kernel(MgspView v, cons
 		if((int) threadIdx.x < v.world && (int) threadIdx.x != v.rank) {
 			InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, threadIdx.x, par, v.rank));
 			h->key_count = n3 / 3;
+			h->max_vel_sq = *local_max_vel;
+			__threadfence_system();
+			st_release_sys(&h->flag_keys, epoch);
+		}
+		if(threadIdx.x == 0) v.done[2] = 0;
+	}
+}
+
+// Step-driver form: clears this rank's next grid (new numbering) and publishes the keys in ONE launch.  The flag goes out only
+// after every CTA has finished both loops, so a peer that sees it may reduce into the cleared grid (the order the two separate
+// kernels had).
+__global__ void __launch_bounds__(256) mgsp_clear_publish_kernel(MgspView v, const int* keys, const int* key_count, const float* local_max_vel, float* clear_grid) {
+	const int epoch = v.epochs[2] + 1, par = epoch & 1;
+	const int nk = min(*key_count, v.L.max_blocks);
+	{
+		const size_t n4 = (size_t) nk * (kGridBlockFloats / 4);
+		float4* g = reinterpret_cast<float4*>(clear_grid);
+		for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	const int n3 = nk * 3;
+	for(int p = 0; p < v.world; ++p) {
+		if(p == v.rank) continue;
+		int* rk = reinterpret_cast<int*>(seg_of(v, p, par, v.rank) + v.L.off_keys);
+		for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) rk[i] = keys[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	__shared__ int s_last;
+	if(threadIdx.x == 0) s_last = atomicAdd(&v.done[2], 1) == (int) gridDim.x - 1;
+	__syncthreads();
+	if(s_last) {
+		__threadfence_system();
+		if((int) threadIdx.x < v.world && (int) threadIdx.x != v.rank) {
+			InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, threadIdx.x, par, v.rank));
+			h->key_count = nk;
 			h->max_vel_sq = *local_max_vel;
 			__threadfence_system();
 			st_release_sys(&h->flag_keys, epoch);

@@ -48,8 +48,22 @@ def connect(sim, dist=None):
     dist.barrier()
 
 
+def common_max_blocks(n_local, dist=None, factor=5.0):
+    """Block capacity that EVERY rank must use (the inbox layout is computed from it on both sides of a transfer): sized for the
+    largest shard."""
+    n = int(n_local)
+    if dist is not None and dist.is_initialized():
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = int(t.item())
+    return int(max(4000, n / 512 * factor))
+
+
 def build_rank_sim(scene_part, rank, world, dt, max_blocks, apply_material=None, stream=None, use_graph=True, max_ppc=128, halo_cap=0):
     """One rank's simulator with ITS particle sets registered (MgspBenchmark::init_model(did, positions), mgsp_benchmark.cuh:240-307).
+    max_blocks / halo_cap / max_ppc must be the same on every rank (see common_max_blocks).
     apply_material(sim, model_id, material, dx) sets the material parameters (default: claymore_b200.scenes.apply_material)."""
     from . import scenes
     if apply_material is None:

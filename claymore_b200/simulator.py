@@ -16,6 +16,7 @@ class GmpmSimulator:
     DEFAULT_DT = 1e-4     # gmpm_simulator.cuh:24
     DEFAULT_FPS = 24      # :25
     DEFAULT_FRAMES = 60   # :26
+    MGSP_HANDLE_BYTES = 160   # CB200_MGSP_HANDLE_BYTES
 
     def __init__(self, gpu=0, dt=DEFAULT_DT, fps=DEFAULT_FPS, frames=DEFAULT_FRAMES, config=None, max_blocks=10000, use_graph=True,
                  stream=None, mgsp_rank=0, mgsp_world=1, mgsp_halo_cap=0, auto_grow=None):
@@ -162,13 +163,13 @@ class GmpmSimulator:
 
     # ---- MGSP peer wiring (one process per GPU: exchange the 64-byte IPC handles with any host all-gather) ----------
     def mgsp_ipc_handle(self):
-        buf = (C.c_ubyte * 128)()
+        buf = (C.c_ubyte * self.MGSP_HANDLE_BYTES)()
         check(self.L.cb200_sim_mgsp_ipc_handle(self.h, buf), "mgsp_ipc_handle")
         return bytes(buf)
 
     def mgsp_open_peers(self, handles_by_rank):
         blob = b"".join(handles_by_rank)
-        assert len(blob) == 128 * self.mgsp_world
+        assert len(blob) == self.MGSP_HANDLE_BYTES * self.mgsp_world
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         check(self.L.cb200_sim_mgsp_open_peers(self.h, buf), "mgsp_open_peers")
 

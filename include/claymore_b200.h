@@ -215,8 +215,12 @@ CB200_API int cb200_sim_profile_phases(cb200_sim* sim, double* out_ms);
  * calls per sub-step.  Setup: every rank publishes its inbox handle, all ranks open all handles (any host-side
  * all-gather: torch.distributed here), then initial_setup / step run as in the single-GPU case. */
 CB200_API int cb200_sim_mgsp_inbox(cb200_sim* sim, void** inbox, void** next_grid, size_t* inbox_bytes);
-CB200_API int cb200_sim_mgsp_ipc_handle(cb200_sim* sim, void* handle128);                 /* two cudaIpcMemHandle_t: inbox, next grid */
-CB200_API int cb200_sim_mgsp_open_peers(cb200_sim* sim, const void* handles128_by_rank);  /* world x 128 bytes */
+/* EVERY rank must be created with the same max_blocks, mgsp_halo_cap, mgsp_world and cb200_config: the layout of the messages in a
+ * peer's inbox is computed from them on both sides.  The handle blob carries them and open_peers returns cudaErrorInvalidValue on a
+ * mismatch (same-process peers wired with set_peers are the caller's responsibility). */
+#define CB200_MGSP_HANDLE_BYTES 160
+CB200_API int cb200_sim_mgsp_ipc_handle(cb200_sim* sim, void* handle);                 /* CB200_MGSP_HANDLE_BYTES: two cudaIpcMemHandle_t (inbox, next grid) + layout words */
+CB200_API int cb200_sim_mgsp_open_peers(cb200_sim* sim, const void* handles_by_rank);  /* world x CB200_MGSP_HANDLE_BYTES */
 CB200_API int cb200_sim_mgsp_set_peers(cb200_sim* sim, void* const* inbox_ptrs_by_rank, void* const* next_grid_ptrs_by_rank); /* same-process peers */
 /* halo statistics of the current partition (synchronises): blocks shared with each rank, halo particle blocks */
 CB200_API int cb200_sim_mgsp_halo_counts(cb200_sim* sim, int* shared_blocks_by_rank, int* halo_particle_blocks);

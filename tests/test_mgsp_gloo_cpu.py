@@ -33,10 +33,10 @@ def _worker(rank, world, port, q):
         counts = [None] * world
         dist.all_gather_object(counts, n_local)
         assert sum(counts) == len(scene["models"][0]["pos"]) and max(counts) - min(counts) <= 1
-        # the 128-byte handle exchange of mgsp.connect(), with stand-in handles
+        # the 160-byte handle exchange of mgsp.connect(), with stand-in handles
         handles = [None] * world
-        dist.all_gather_object(handles, bytes([rank]) * 128)
-        assert [h[0] for h in handles] == list(range(world)) and all(len(h) == 128 for h in handles)
+        dist.all_gather_object(handles, bytes([rank]) * 160)
+        assert [h[0] for h in handles] == list(range(world)) and all(len(h) == 160 for h in handles)
         # halo protocol with gloo as the transport: keys all-gather, block exchange, reduce
         sim = scenes.build_oracle(ob, part)
         cfg = sim.cfg
