@@ -452,7 +452,7 @@ def mgsp_parity(sim, part, scene, args, rank, world, mb_single, max_ppc, stream,
     # entered a rank's partition in the last sub-step was not yet tagged as shared when that sub-step's g2p2g ran, so that rank's
     # copy is still all zero for this one sub-step.  It is never read: a particle's next G2P stencil lies inside its previous
     # block's 2x2x2 neighbourhood, i.e. in blocks its rank already had.  Such copies are counted, every other copy must agree.
-    fresh = dup & (mass[order] == 0.0) & (np.abs(mom[order]).sum(1) == 0.0)
+    fresh = dup & (mass[order] == 0.0) & (np.abs(mom[order]).sum(1) == 0.0) & (ref_mass != 0.0)
     chk = dup & ~fresh
     scale_m = max(float(np.abs(mass).max()), 1e-30)
     scale_p = max(float(np.abs(mom).max()), 1e-30)

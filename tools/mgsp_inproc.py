@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--split", default="global")
     ap.add_argument("--max-ppc", type=int, default=128)
     ap.add_argument("--check-every", type=int, default=0)
+    ap.add_argument("--diagnose", action="store_true")
     a = ap.parse_args()
     from claymore_b200 import mgsp, scenes
     scene, label = scenes.workload(a.workload)
@@ -52,21 +53,38 @@ def main():
     assert not errs and not any(t.is_alive() for t in th), errs
     print("setup ok", flush=True)
     def owners(label):
-        allh, allg = [], []
-        for s in sims:
+        allh, allg, rk, idx, pbcs, allkeys = [], [], [], [], [], []
+        for r, s in enumerate(sims):
             s.sync()
             st = s.stats()
             k, g = s.active_keys()[: st.neighbor_block_count], s.grid()
             allh.append(scenes.key_hash(k))
             allg.append(g)
+            rk.append(np.full(len(k), r))
+            idx.append(np.arange(len(k)))
+            pbcs.append(st.particle_block_count)
+            allkeys.append(k)
         h = np.concatenate(allh)
         g = np.concatenate(allg, 0)
+        if a.diagnose:
+            rk_, idx_, keys_ = np.concatenate(rk), np.concatenate(idx), np.concatenate(allkeys, 0)
+            o = np.lexsort((-np.abs(g).sum(axis=(1, 2)), h))
+            hs, gs = h[o], g[o]
+            first = np.ones(len(hs), bool)
+            first[1:] = hs[1:] != hs[:-1]
+            fresh = ~first & (np.abs(gs).max(axis=(1, 2)) == 0)
+            ii = np.nonzero(fresh)[0][:12]
+            for i in ii:
+                j = i - 1   # the fullest copy of the same key
+                while not first[j]:
+                    j -= 1
+                print(f"   key {keys_[o][i]} zero on rank {rk_[o][i]} (block {idx_[o][i]}, pbc {pbcs[rk_[o][i]]}); full on rank {rk_[o][j]} (block {idx_[o][j]}, pbc {pbcs[rk_[o][j]]}) mass {gs[j, 0].sum():.3e} max cell {gs[j, 0].max():.3e}")
         o = np.lexsort((-np.abs(g).sum(axis=(1, 2)), h))   # per key the fullest copy first
         hs, gs = h[o], g[o]
         first = np.ones(len(hs), bool)
         first[1:] = hs[1:] != hs[:-1]
         grp = np.cumsum(first) - 1
-        fresh = ~first & (np.abs(gs).max(axis=(1, 2)) == 0)   # new on that rank in this sub-step: not yet tagged, never read (see bench.mgsp_parity)
+        fresh = ~first & (np.abs(gs).max(axis=(1, 2)) == 0) & (np.abs(gs[first][grp]).max(axis=(1, 2)) > 0)   # new on that rank in this sub-step: not yet tagged, never read (see bench.mgsp_parity)
         bad = (np.abs(gs - gs[first][grp]).max(axis=(1, 2)) > 1e-4 * np.abs(gs).max()) & ~fresh
         print(label, "shared", int((~first).sum()), "fresh", int(fresh.sum()), "disagreeing", int(bad.sum()), "blocks", [s.block_counts() for s in sims], flush=True)
         return int(bad.sum())
@@ -99,7 +117,7 @@ def main():
     first = np.ones(len(hs), bool)
     first[1:] = hs[1:] != hs[:-1]
     grp = np.cumsum(first) - 1
-    fresh = ~first & (np.abs(gs).max(axis=(1, 2)) == 0)
+    fresh = ~first & (np.abs(gs).max(axis=(1, 2)) == 0) & (np.abs(gs[first][grp]).max(axis=(1, 2)) > 0)
     owner_err = (np.abs(gs - gs[first][grp]).max(axis=(1, 2))[~fresh]).max() / np.abs(gs).max()
     print("shared blocks", int((~first).sum()), "max owners", int(np.bincount(grp).max()), "owner err", owner_err)
     assert np.array_equal(hs[first], sh), "key sets differ"
