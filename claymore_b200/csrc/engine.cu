@@ -663,6 +663,7 @@ void preload_kernels() {
 	preload(build_particle_cell_buckets_kernel);
 	preload(array_to_buffer_kernel);
 	preload(rasterize_kernel);
+	preload(rasterize_blocks_kernel);
 	preload(init_adv_bucket_kernel);
 	preload(retrieve_kernel);
 	preload(collect_halo_blockids_kernel);
@@ -1061,7 +1062,7 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	clear_grid_kernel<<<blocks_for((long long) nbc * 64, 256), 256, 0, st>>>(nbc, s->grid[0]);
 	++s->launches;
 	for(Model& m : s->models) {
-		rasterize_kernel<<<blocks_for(m.n, 256), 256, 0, st>>>(cfg, m.n, m.d_pos, s->grid[0], s->part[R].index_table, m.pb[R].mass, m.v0[0], m.v0[1], m.v0[2], err);
+		rasterize_blocks_kernel<<<blocks_for(pbc, 1), 256, 0, st>>>(cfg, m.material, pbc, s->part[R].active_keys, s->part[R].index_table, view(m.pb[R]), s->grid[0], m.pb[R].mass, m.v0[0], m.v0[1], m.v0[2], err);
 		init_adv_bucket_kernel<<<blocks_for(pbc, 1), 128, 0, st>>>(cfg, pbc, m.pb[Rn].particle_bucket_sizes, m.pb[Rn].blockbuckets);
 		s->launches += 2;
 	}

@@ -554,13 +554,20 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				else cr2 = cr;
 			}
 			cp_async_wait<0>();
-			if(acc_dirty && tid < 8) tma_wait_read<0>();  // the TMA unit has read the arena of the previous block
-			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete
 			if(acc_dirty) {
-				float4* acc4 = reinterpret_cast<float4*>(sm.acc);
-				for(int i = tid; i < 8 * 256 / 4; i += T) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+				// The arena still feeds the previous block's bulk reductions.  The LAST warp drains and zeroes it: with 512 particles
+				// on 192 threads that warp has no particle in the third pass, so the drain rides in its idle time instead of sitting
+				// between two barriers of the whole CTA (its threads issued the reductions, see the flush below).
+				if(tid >= T - 32) {
+					if(tid < T - 24) tma_wait_read<0>();  // the TMA unit has read the arena
+					__syncwarp();
+					float4* acc4 = reinterpret_cast<float4*>(sm.acc);
+#pragma unroll 4
+					for(int i = tid - (T - 32); i < 8 * 256 / 4; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+				}
 				acc_dirty = false;
 			}
+			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete; the arena is zero
 			// exclusive scan of the 64 cell counts, redundantly in every warp (lane l holds cells 2l and 2l+1): no barrier,
 			// no shared prefix array
 			const int lane = tid & 31;
@@ -607,6 +614,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 #pragma unroll
 				for(int n9 = 0; n9 < 9; ++n9) acc01[n9] = acc23[n9] = mk2(0.f, 0.f);
 				const f2 c01 = mk2(0.f, 1.f);
+#ifdef CB200_P2_UNROLL
+#pragma unroll CB200_P2_UNROLL
+#endif
 				for(int p = 0; p < n; ++p) {
 					const int slot = rec_slot(sm.idx[st + p]);
 					const float4 r0 = sm.rec[0][slot];  // (y, z, x, code)
@@ -720,7 +730,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		}  // models
 
 		// ---- arena -> next grid: eight 1-KiB bulk add-reductions ----------------------------------
-		const int flush_bno = tid < 8 ? sm.nbr[(((tid >> 2) & 1) + 1) * 9 + (((tid >> 1) & 1) + 1) * 3 + (tid & 1) + 1] : -1;
+		const int ft = tid - (T - 32);  // the flush is issued by the first eight lanes of the LAST warp (they also drain it, see above)
+		const int flush_bno = (ft >= 0 && ft < 8) ? sm.nbr[(((ft >> 2) & 1) + 1) * 9 + (((ft >> 1) & 1) + 1) * 3 + (ft & 1) + 1] : -1;
 		fence_proxy_async();
 		if(tid == 0) {  // queue shift: every thread read cur/next at the top of this block, barriers ago
 			sm.cur_blk = qn;
@@ -728,24 +739,24 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 		}
 		__syncthreads();  // B6: arena, records and neighbour tables of this block are no longer written or read by the SM
 		if(tid == 0) sm.nmovers = 0;
-		if(tid < 8) {
+		if(ft >= 0 && ft < 8) {
 			const int bno = flush_bno;
 			if(bno >= 0) {
-				tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + tid * 256, 1024);
+				tma_reduce_add_f32(a.next_grid + (size_t) bno * kGridBlockFloats, sm.acc + ft * 256, 1024);
 				if(a.overlap_marks) {
 					unsigned mask = (unsigned) a.overlap_marks[bno];
 					while(mask) {
 						const int p = __ffs(mask) - 1;
 						mask &= mask - 1;
 						const int rb = a.peer_bno[(size_t) p * a.peer_stride + bno];
-						if(rb >= 0) tma_reduce_add_f32(a.peer_grid[p] + (size_t) rb * kGridBlockFloats, sm.acc + tid * 256, 1024);
+						if(rb >= 0) tma_reduce_add_f32(a.peer_grid[p] + (size_t) rb * kGridBlockFloats, sm.acc + ft * 256, 1024);
 					}
 				}
 			}
 			tma_commit();  // not waited for here: see acc_dirty
 		}
 	}
-	if(threadIdx.x < 8) tma_wait_all<0>();
+	if((int) threadIdx.x >= kG2P2GThreads - 32 && (int) threadIdx.x < kG2P2GThreads - 24) tma_wait_all<0>();
 }
 
 }  // namespace cb200

@@ -93,6 +93,67 @@ __global__ void rasterize_kernel(Cfg cfg, int n, const float* pos, float* grid, 
 	}
 }
 
+// Block-parallel form of rasterize for the step driver: the particles are already bucketed per block and sit in the bins, so a
+// CTA accumulates the MASS of one particle block's particles in a shared-memory arena (2x2x2 grid blocks, as g2p2g) and flushes
+// it once: 4 global atomics per touched node instead of 108 per particle (the momentum of a model is v0 x its mass field, since
+// every particle of a model starts with the same velocity, :212-215).
+__global__ void __launch_bounds__(256) rasterize_blocks_kernel(Cfg cfg, int material, int block_count, const int* keys, const int* table, PBuf pb, float* grid, float mass, float v0x, float v0y, float v0z, int* error) {
+	__shared__ float arena[8 * 64];
+	__shared__ int s_bno[8];
+	const int binf = material == CB200_J_FLUID ? 128 : 512;
+	for(int b = blockIdx.x; b < block_count; b += gridDim.x) {
+		const int n = pb.particle_bucket_sizes[b];
+		if(n == 0) continue;
+		const int kx = keys[3 * b], ky = keys[3 * b + 1], kz = keys[3 * b + 2];
+		for(int i = threadIdx.x; i < 512; i += blockDim.x) arena[i] = 0.f;
+		if(threadIdx.x < 8) s_bno[threadIdx.x] = table_query(cfg, table, kx + ((threadIdx.x >> 2) & 1), ky + ((threadIdx.x >> 1) & 1), kz + (threadIdx.x & 1));
+		__syncthreads();
+		const float* bins = pb.bins + (size_t) pb.bin_offsets[b] * binf;
+		for(int i = threadIdx.x; i < n; i += blockDim.x) {
+			const float* bin = bins + (size_t) (i >> 5) * binf + (i & 31);
+			int ab[3];
+			float w[3][3];
+#pragma unroll
+			for(int d = 0; d < 3; ++d) {
+				const float x = bin[32 * d];
+				const int base = cell_index(cfg, x) - 1;
+				bspline_weights((x - base * cfg.dx) * cfg.dx_inv, w[d][0], w[d][1], w[d][2]);
+				ab[d] = base - 4 * (d == 0 ? kx : (d == 1 ? ky : kz));  // 1..4: node index inside the 8^3 arena
+			}
+			if(((unsigned) (ab[0] - 1) > 3u) | ((unsigned) (ab[1] - 1) > 3u) | ((unsigned) (ab[2] - 1) > 3u)) {  // not a particle of this block
+				if(error) atomicOr(error, kErrLostParticle);
+				continue;
+			}
+#pragma unroll
+			for(int i3 = 0; i3 < 3; ++i3)
+#pragma unroll
+				for(int j = 0; j < 3; ++j)
+#pragma unroll
+					for(int k = 0; k < 3; ++k) {
+						const int X = ab[0] + i3, Y = ab[1] + j, Z = ab[2] + k;
+						const int bi = ((X >> 2) << 2) | ((Y >> 2) << 1) | (Z >> 2);
+						atomicAdd(&arena[bi * 64 + (((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3))], mass * (w[0][i3] * w[1][j] * w[2][k]));
+					}
+		}
+		__syncthreads();
+		for(int i = threadIdx.x; i < 512; i += blockDim.x) {
+			const float m = arena[i];
+			if(m == 0.f) continue;
+			const int bno = s_bno[i >> 6];
+			if(bno < 0) {
+				if(error) atomicOr(error, kErrLostParticle);
+				continue;
+			}
+			float* cell = grid + (size_t) bno * kGridBlockFloats + (i & 63);
+			atomicAdd(cell, m);
+			atomicAdd(cell + 64, m * v0x);
+			atomicAdd(cell + 128, m * v0y);
+			atomicAdd(cell + 192, m * v0z);
+		}
+		__syncthreads();
+	}
+}
+
 // init_adv_bucket (mgmpm_kernels.cuh:96-104): identity tags (dir 13 == no block change)
 __global__ void init_adv_bucket_kernel(Cfg cfg, int block_count, const int* sizes, int* buckets) {
 	for(int b = blockIdx.x; b < block_count; b += gridDim.x)
