@@ -242,7 +242,7 @@ def device_timed(scene, args, stream, mb, max_ppc, clocks=None):
                 nbc=st.neighbor_block_count, ebc=st.exterior_block_count)
 
 
-def roofline_of(scene, res, steps):
+def roofline_of(scene, res, steps, workload_name=None):
     per_model = [len(m["pos"]) for m in scene["models"]]
     mats = [m["material"] for m in scene["models"]]
     alg_step, n_mat = g2p2g_alg_bytes(per_model, mats, res["pbc"])
@@ -261,7 +261,7 @@ def roofline_of(scene, res, steps):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
-                r["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                r["traffic"] = json.load(f).get("by_workload", {}).get(workload_name, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
     return r
@@ -371,7 +371,7 @@ def run_b200(args):
     res = device_timed(scene, args, stream, mb, max_ppc, clocks)
     clk = clocks.stop()
     value = n_particles * args.steps / (res["ms_total"] * 1e-3) / 1e6
-    roofline = roofline_of(scene, res, args.steps)
+    roofline = roofline_of(scene, res, args.steps, args.workload)
     e2e = e2e_single(scene, args, stream, mb, max_ppc)
 
     # ---- the reference's own kernels on the same scene, same GPU (the ">= 2x per GPU" denominator) ---------------------
@@ -391,7 +391,7 @@ def run_b200(args):
         r5 = device_timed(sc5, args, stream, scenes.max_blocks_for(sc5), 128)
         n5 = scenes.n_particles(sc5)
         configs1 = {"workload": lab5, "value": n5 * args.steps / (r5["ms_total"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": r5["ms_total"] / args.steps,
-                    "roofline_frac": roofline_of(sc5, r5, args.steps)["frac"]}
+                    "roofline_frac": roofline_of(sc5, r5, args.steps, "spheres5m")["frac"]}
 
     # ---- CPU baseline beside it: the oracle port on the host cores, bounded sample ---------------------------------------
     cpu = None

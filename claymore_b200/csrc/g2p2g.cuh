@@ -87,7 +87,7 @@ struct G2P2GSmem {
 	float acc[8 * 256];              // accumulation arena (grid-block layout)
 	float4 rec[4][kChunk];           // staged P2G records, SoA over the 4 quads; 6 KiB of quad 1 double as the TMA landing
 	                                 // zone (8 blocks x 3 channels x 64 cells) while a block's neighbourhood is staged
-	unsigned short idx[kChunk];      // staged slots sorted by cell
+	unsigned short idx[kChunk];      // (swizzled) record slots sorted by cell
 	unsigned short movers[kChunk];   // staged slots of particles that changed cell
 	int cnt[64];
 	int nbr[27];
@@ -358,15 +358,14 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					f2 vyz = z2, A12 = z2, A45 = z2, A78 = z2, vxA6 = z2;
 					float A0 = 0.f, A3 = 0.f;
 					const float4* vp = &sm.vel4[(ab[0] * 8 + ab[1]) * 8 + ab[2]];
-					const float dxn = lp[0] * dx_inv;
-					// the x planes are a real loop (its weight comes from the polynomial form): unrolled, the scheduler hoists all 27
-					// LDS.128 of the stencil and spills
+					// The x planes are a real loop: unrolled (even behind a compiler fence) the scheduler hoists all 27 LDS.128 of the stencil
+					// and spills.  The plane's weight rotates through three registers instead of being selected by the loop index.
+					float wx, wx_n, wx_nn;
+					bspline_weights(lp[0] * dx_inv, wx, wx_n, wx_nn);
+					float xi = -lp[0];
 #pragma unroll 1
 					for(int i = 0; i < 3; ++i, vp += 64) {
-						float pa, pb, pc;
-						bspline_poly(i, pa, pb, pc);
-						const float wx = pa + dxn * (pb + pc * dxn);
-						const float wxx = wx * ((float) i * dx - lp[0]);
+						const float wxx = wx * xi;
 						f2 Ryz = z2, Yyz = z2, Zyz = z2, RxZx = z2;
 						float Yx = 0.f;
 #pragma unroll
@@ -392,6 +391,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						vxA6 = fma2(RxZx, wx, vxA6);
 						A0 = fmaf(wxx, RxZx.x, A0);
 						A3 = fmaf(wx, Yx, A3);
+						wx = wx_n;
+						wx_n = wx_nn;
+						xi += dx;
 					}
 					velx = vxA6.x;
 					velyz = vyz;
@@ -585,9 +587,10 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			};
 			{
 				const int s0 = cell_start(max(cr0, 0) >> 16), s1 = cell_start(max(cr1, 0) >> 16), s2 = cell_start(max(cr2, 0) >> 16);
-				if(cr0 >= 0) sm.idx[s0 + (cr0 & 0xffff)] = (unsigned short) tid;
-				if(cr1 >= 0) sm.idx[s1 + (cr1 & 0xffff)] = (unsigned short) (T + tid);
-				if(cr2 >= 0) sm.idx[s2 + (cr2 & 0xffff)] = (unsigned short) (2 * T + tid);
+				// (the swizzled record slot is stored: phase 2 reads it three times per particle, once per x-slice)
+				if(cr0 >= 0) sm.idx[s0 + (cr0 & 0xffff)] = (unsigned short) rec_slot(tid);
+				if(cr1 >= 0) sm.idx[s1 + (cr1 & 0xffff)] = (unsigned short) rec_slot(T + tid);
+				if(cr2 >= 0) sm.idx[s2 + (cr2 & 0xffff)] = (unsigned short) rec_slot(2 * T + tid);
 			}
 
 			// ================= phase 2: cell-parallel accumulation =====================================
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 #pragma unroll CB200_P2_UNROLL
 #endif
 				for(int p = 0; p < n; ++p) {
-					const int slot = rec_slot(sm.idx[st + p]);
+					const int slot = sm.idx[st + p];
 					const float4 r0 = sm.rec[0][slot];  // (y, z, x, code)
 					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
 					const float4 r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];
