@@ -363,8 +363,12 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					float wx, wx_n, wx_nn;
 					bspline_weights(lp[0] * dx_inv, wx, wx_n, wx_nn);
 					float xi = -lp[0];
+#ifdef CB200_ABLATE_G2P
+					for(int i = 0; i < 1; ++i, vp += 64) {
+#else
 #pragma unroll 1
 					for(int i = 0; i < 3; ++i, vp += 64) {
+#endif
 						const float wxx = wx * xi;
 						f2 Ryz = z2, Yyz = z2, Zyz = z2, RxZx = z2;
 						float Yx = 0.f;
@@ -481,7 +485,12 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 							dbin[(4 + 3 * c) * 32] = F.p[c].x;
 							dbin[(5 + 3 * c) * 32] = F.p[c].y;
 						}
+#ifdef CB200_ABLATE_STRESS
+						S = F;
+						if(false) {
+#else
 						if(!stress_fixed_corotated_polar_packed(M.mat, F, S)) {
+#endif
 							float Fa[9], PFa[9];
 							m3p_to_array(F, Fa);
 							stress_fixed_corotated(M.mat, Fa, PFa);
@@ -617,10 +626,11 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 #pragma unroll
 				for(int n9 = 0; n9 < 9; ++n9) acc01[n9] = acc23[n9] = mk2(0.f, 0.f);
 				const f2 c01 = mk2(0.f, 1.f);
-#ifdef CB200_P2_UNROLL
-#pragma unroll CB200_P2_UNROLL
+#ifdef CB200_ABLATE_P2   // timing experiment only (results are wrong): what does the cell-parallel accumulation cost end to end?
+				for(int p = 0; p < 0; ++p) {
+#else
+				for(int p = 0; p < n; ++p) {  // (requesting the next particle's index / first quad one iteration ahead measured 0.8 % slower)
 #endif
-				for(int p = 0; p < n; ++p) {
 					const int slot = sm.idx[st + p];
 					const float4 r0 = sm.rec[0][slot];  // (y, z, x, code)
 					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
