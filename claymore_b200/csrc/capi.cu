@@ -39,10 +39,18 @@ static int g2p2g_blocks_per_sm() {
 	static int cache[kMaxDevices] = {};  // the shared-memory opt-in is per device (function attributes are per context)
 	int& v = cache[current_device()];
 	if(!v) {
-		cudaFuncSetAttribute(g2p2g_kernel<MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(G2P2GSmem));
-		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, g2p2g_kernel<MAT>, kG2P2GThreads, sizeof(G2P2GSmem)) != cudaSuccess || v <= 0) v = 3;
+		cudaFuncSetAttribute(g2p2g_kernel<MAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(G2P2GSmem));
+		cudaFuncSetAttribute(g2p2g_kernel<MAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(G2P2GSmem));
+		int u = 0;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, g2p2g_kernel<MAT, false>, kG2P2GThreads, sizeof(G2P2GSmem)) != cudaSuccess || v <= 0) v = 3;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&u, g2p2g_kernel<MAT, true>, kG2P2GThreads, sizeof(G2P2GSmem)) == cudaSuccess && u > 0 && u < v) v = u;
 	}
 	return v;
+}
+template<int MAT>
+static void g2p2g_launch_one(const G2P2GArgs& a, bool sorted, int grid, cudaStream_t s) {
+	if(sorted) g2p2g_kernel<MAT, true><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a);
+	else g2p2g_kernel<MAT, false><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a);
 }
 
 // resolves occupancy / shared-memory attributes of every material up front (see preload_kernels in engine.cu)
@@ -66,11 +74,13 @@ cudaError_t launch_g2p2g(int material, const G2P2GArgs& a, int block_hint, cudaS
 	int grid = num_sms() * per_sm;
 	if(block_hint >= 0 && block_hint < grid) grid = block_hint;
 	if(grid < 1) return cudaSuccess;
+	bool sorted = a.n_models > 0;  // the cell-offset form needs the offsets of every model of the launch
+	for(int m = 0; m < a.n_models; ++m) sorted &= a.m[m].next_offs != nullptr;
 	switch(material) {
-		case CB200_J_FLUID: g2p2g_kernel<CB200_J_FLUID><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
-		case CB200_FIXED_COROTATED: g2p2g_kernel<CB200_FIXED_COROTATED><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
-		case CB200_SAND: g2p2g_kernel<CB200_SAND><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
-		case CB200_NACC: g2p2g_kernel<CB200_NACC><<<grid, kG2P2GThreads, sizeof(G2P2GSmem), s>>>(a); break;
+		case CB200_J_FLUID: g2p2g_launch_one<CB200_J_FLUID>(a, sorted, grid, s); break;
+		case CB200_FIXED_COROTATED: g2p2g_launch_one<CB200_FIXED_COROTATED>(a, sorted, grid, s); break;
+		case CB200_SAND: g2p2g_launch_one<CB200_SAND>(a, sorted, grid, s); break;
+		case CB200_NACC: g2p2g_launch_one<CB200_NACC>(a, sorted, grid, s); break;
 	}
 	return cudaGetLastError();
 }
@@ -100,6 +110,7 @@ int cb200_g2p2g(const cb200_config* c, float dt, float new_dt, int pbc, cb200_pa
 	a.m[0].cur = view(cur);
 	a.m[0].next = view(next);
 	a.m[0].mat = mat_of(cur);
+	a.m[0].next_offs = nullptr;  // the caller's bucket may be in any order (the reference's is atomics-dependent)
 	a.prev_table = prev_partition.index_table;
 	a.table = partition.index_table;
 	a.keys = partition.active_keys;

@@ -177,6 +177,7 @@ struct Model {
 	int n = 0;
 	float v0[3] = {0, 0, 0};
 	int* bin_sizes = nullptr;
+	unsigned short* celloffs[2] = {nullptr, nullptr};  // per buffer: start of every cell inside the (cell-major) block bucket, [blocks][64]
 	// output staging (retrieve): device buffer + pinned host mirror, grown on demand, reused across frames
 	float* d_out = nullptr;
 	float* h_out = nullptr;
@@ -313,6 +314,7 @@ G2P2GArgs make_g2p2g_args(cb200_sim* s, int material, int R, int halo_mode) {
 		gm.cur = view(m.pb[R]);
 		gm.next = view(m.pb[Rn]);
 		gm.mat = mat_of(m.pb[R]);
+		gm.next_offs = m.celloffs[Rn];  // the buckets of the driver are cell-major: phase 2 takes its particle ranges from these offsets
 	}
 	a.prev_table = s->part[Rn].index_table;
 	a.table = s->part[R].index_table;
@@ -432,6 +434,7 @@ int enqueue_rebuild(cb200_sim* s, int R) {
 			a.dst_sizes[m] = s->models[m].pb[R].particle_bucket_sizes;
 			a.dst_buckets[m] = s->models[m].pb[R].blockbuckets;
 			a.bin_offsets[m] = s->models[m].pb[R].bin_offsets;
+			a.dst_offs[m] = s->models[m].celloffs[R];
 		}
 		rebuild_kernel<<<tiles, kRebuildThreads, 0, st>>>(a);
 		++s->launches;
@@ -645,10 +648,14 @@ void preload_kernels() {
 	if(dev < 0 || dev >= 64) dev = 0;
 	if(done[dev]) return;
 	done[dev] = true;
-	preload(g2p2g_kernel<CB200_J_FLUID>);
-	preload(g2p2g_kernel<CB200_FIXED_COROTATED>);
-	preload(g2p2g_kernel<CB200_SAND>);
-	preload(g2p2g_kernel<CB200_NACC>);
+	preload(g2p2g_kernel<CB200_J_FLUID, false>);
+	preload(g2p2g_kernel<CB200_FIXED_COROTATED, false>);
+	preload(g2p2g_kernel<CB200_SAND, false>);
+	preload(g2p2g_kernel<CB200_NACC, false>);
+	preload(g2p2g_kernel<CB200_J_FLUID, true>);
+	preload(g2p2g_kernel<CB200_FIXED_COROTATED, true>);
+	preload(g2p2g_kernel<CB200_SAND, true>);
+	preload(g2p2g_kernel<CB200_NACC, true>);
 	preload(grid_update_kernel);
 	preload(clear_grid_kernel);
 	preload(carry_grid_kernel);
@@ -770,6 +777,7 @@ int cb200_sim_reserve(cb200_sim* s, int new_max_blocks) {
 			CK(grow_array(s, pb.bin_offsets, ob + 2, nb + 2, 0));
 		}
 		CK(grow_array(s, m.bin_sizes, ob + 2, nb + 2, 0));
+		for(int i = 0; i < 2; ++i) CK(grow_array(s, m.celloffs[i], (ob + 1) * kBlockVol, (nb + 1) * kBlockVol, 0));
 		m.bin_capacity = new_bins;
 	}
 	s->desc.max_blocks = new_max_blocks;
@@ -880,6 +888,8 @@ int cb200_sim_destroy(cb200_sim* s) {
 		}
 		g_pool.release(m.d_pos);
 		g_pool.release(m.bin_sizes);
+		g_pool.release(m.celloffs[0]);
+		g_pool.release(m.celloffs[1]);
 		g_pool.release(m.d_out);
 		cudaFreeHost(m.h_out);
 	}
@@ -931,6 +941,10 @@ int cb200_sim_init_model(cb200_sim* s, int material, const float* positions_host
 	}
 	CK(pool_alloc(&m.bin_sizes, (mb + 2) * sizeof(int)));
 	CK(cudaMemsetAsync(m.bin_sizes, 0, (mb + 2) * sizeof(int), s->stream));
+	for(int i = 0; i < 2; ++i) {
+		CK(pool_alloc(&m.celloffs[i], (mb + 1) * kBlockVol * sizeof(unsigned short)));
+		CK(cudaMemsetAsync(m.celloffs[i], 0, (mb + 1) * kBlockVol * sizeof(unsigned short), s->stream));
+	}
 	CK(pool_alloc(&m.d_pos, (size_t) n * 3 * sizeof(float)));
 	CK(cudaMemcpyAsync(m.d_pos, positions_host, (size_t) n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
@@ -1001,7 +1015,7 @@ int cb200_sim_initial_setup(cb200_sim* s) {
 	if(pbc > cap) return (int) cudaErrorMemoryAllocation;
 	for(Model& m : s->models) {
 		build_particle_cell_buckets_kernel<<<blocks_for(m.n, 256), 256, 0, st>>>(cfg, m.n, m.d_pos, view(m.pb[R]), s->part[Rn].index_table, err);
-		cell_bucket_to_block_kernel<<<blocks_for(pbc, 1), kBucketThreads, 0, st>>>(cfg, pbc, m.pb[R].cell_particle_counts, m.pb[R].cellbuckets, m.pb[R].particle_bucket_sizes, m.pb[R].blockbuckets);
+		cell_bucket_to_block_kernel<<<blocks_for(pbc, 1), kBucketThreads, 0, st>>>(cfg, pbc, m.pb[R].cell_particle_counts, m.pb[R].cellbuckets, m.pb[R].particle_bucket_sizes, m.pb[R].blockbuckets, m.celloffs[Rn]);
 		compute_bin_capacity_kernel<<<blocks_for(pbc + 1, 256), 256, 0, st>>>(pbc + 1, m.pb[R].particle_bucket_sizes, m.bin_sizes);
 		ScanArgs a {};
 		a.count = count_imm(pbc + 1);

@@ -49,6 +49,9 @@ constexpr int kChunk = 512;         // particles staged per pass (64 cells x 8 p
 struct G2P2GModel {
 	PBuf cur, next;
 	Mat mat;
+	// nullable: start of every cell inside next.blockbuckets (cell-major buckets of the step driver, [blocks][64]).  With it the staged
+	// chunk is already grouped by home cell: phase 2 takes its particle ranges from these offsets and the counting sort is skipped.
+	const unsigned short* next_offs;
 };
 struct G2P2GArgs {
 	Cfg cfg;
@@ -89,6 +92,7 @@ struct G2P2GSmem {
 	                                 // zone (8 blocks x 3 channels x 64 cells) while a block's neighbourhood is staged
 	unsigned short idx[kChunk];      // (swizzled) record slots sorted by cell
 	unsigned short movers[kChunk];   // staged slots of particles that changed cell
+	unsigned short offs[66];         // SORTED: cell starts of the current model's bucket, [64] = bucket size
 	int cnt[64];
 	int nbr[27];
 	int prevno[27];
@@ -112,7 +116,9 @@ __device__ __forceinline__ void bspline_poly(int i, float& a, float& b, float& c
 	c = i == 1 ? -1.f : 0.5f;
 }
 
-template<int MAT>
+// SORTED: every model's bucket is cell-major and comes with its cell offsets (the step driver); otherwise any bucket order is
+// accepted (kernel-level ABI: the reference's order is atomics-dependent) and the staged particles are counting-sorted by cell.
+template<int MAT, bool SORTED>
 __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_kernel(const G2P2GArgs a) {
 	constexpr int BINF = (MAT == CB200_J_FLUID) ? 128 : 512;
 	constexpr int T = kG2P2GThreads;
@@ -264,6 +270,9 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 
 		for(int c0 = 0; c0 < bucket_size; c0 += kChunk) {
 			const int nchunk = min(kChunk, bucket_size - c0);
+			if constexpr(SORTED) {  // previous readers of sm.offs are behind a barrier (B6 / the arena rounds); B1 publishes the new values
+				if(c0 == 0 && tid <= 64) sm.offs[tid] = tid < 64 ? M.next_offs[(size_t) blk * kBlockVol + tid] : (unsigned short) bucket_size;
+			}
 			{
 				// every chunk after the first of a block waits for the previous one's phase 3; a further model resolves its bins
 				const bool need_srcbin = mi > 0 && c0 == 0;
@@ -363,12 +372,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 					float wx, wx_n, wx_nn;
 					bspline_weights(lp[0] * dx_inv, wx, wx_n, wx_nn);
 					float xi = -lp[0];
-#ifdef CB200_ABLATE_G2P
-					for(int i = 0; i < 1; ++i, vp += 64) {
-#else
 #pragma unroll 1
 					for(int i = 0; i < 3; ++i, vp += 64) {
-#endif
 						const float wxx = wx * xi;
 						f2 Ryz = z2, Yyz = z2, Zyz = z2, RxZx = z2;
 						float Yx = 0.f;
@@ -485,12 +490,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 							dbin[(4 + 3 * c) * 32] = F.p[c].x;
 							dbin[(5 + 3 * c) * 32] = F.p[c].y;
 						}
-#ifdef CB200_ABLATE_STRESS
-						S = F;
-						if(false) {
-#else
 						if(!stress_fixed_corotated_polar_packed(M.mat, F, S)) {
-#endif
 							float Fa[9], PFa[9];
 							m3p_to_array(F, Fa);
 							stress_fixed_corotated(M.mat, Fa, PFa);
@@ -558,11 +558,13 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				sm.rec[2][rs] = make_float4(D.p[1].x, D.p[1].y, D.p[2].x, D.p[2].y);
 				sm.rec[3][rs] = make_float4(q0, D.s[0], D.s[1], D.s[2]);
 				// counting sort by the cell the particle came from (its accumulation home)
-				const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
-				const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);
-				if(it == 0) cr0 = cr;
-				else if(it == 1) cr1 = cr;
-				else cr2 = cr;
+				if constexpr(!SORTED) {
+					const int hc = ((ab[0] - 1) << 4) | ((ab[1] - 1) << 2) | (ab[2] - 1);
+					const int cr = (hc << 16) | atomicAdd(&sm.cnt[hc], 1);
+					if(it == 0) cr0 = cr;
+					else if(it == 1) cr1 = cr;
+					else cr2 = cr;
+				}
 			}
 			cp_async_wait<0>();
 			if(acc_dirty) {
@@ -579,29 +581,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 				acc_dirty = false;
 			}
 			__syncthreads();  // B1: records, cell counts and the mover list of this chunk are complete; the arena is zero
-			// exclusive scan of the 64 cell counts, redundantly in every warp (lane l holds cells 2l and 2l+1): no barrier,
-			// no shared prefix array
 			const int lane = tid & 31;
-			const int c0v = sm.cnt[2 * lane], c1v = sm.cnt[2 * lane + 1];
-			int excl = c0v + c1v;
-#pragma unroll
-			for(int o = 1; o < 32; o <<= 1) {
-				const int t = __shfl_up_sync(0xffffffffu, excl, o);
-				if(lane >= o) excl += t;
-			}
-			excl -= c0v + c1v;
-			auto cell_start = [&](int h) {  // every lane of the warp must call it
-				const int e = __shfl_sync(0xffffffffu, excl, h >> 1), c = __shfl_sync(0xffffffffu, c0v, h >> 1);
-				return e + ((h & 1) ? c : 0);
-			};
-			{
-				const int s0 = cell_start(max(cr0, 0) >> 16), s1 = cell_start(max(cr1, 0) >> 16), s2 = cell_start(max(cr2, 0) >> 16);
-				// (the swizzled record slot is stored: phase 2 reads it three times per particle, once per x-slice)
-				if(cr0 >= 0) sm.idx[s0 + (cr0 & 0xffff)] = (unsigned short) rec_slot(tid);
-				if(cr1 >= 0) sm.idx[s1 + (cr1 & 0xffff)] = (unsigned short) rec_slot(T + tid);
-				if(cr2 >= 0) sm.idx[s2 + (cr2 & 0xffff)] = (unsigned short) rec_slot(2 * T + tid);
-			}
-
 			// ================= phase 2: cell-parallel accumulation =====================================
 			// thread = (home cell hc, x-slice sl of its 3x3x3 stencil); a half-warp holds the 16 cells of one x-plane
 			const int wrp = tid >> 5;
@@ -613,10 +593,40 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 			const int cx = wrp < 3 ? wrp + 1 - hi : (wrp == 3 ? 3 - hi : (wrp == 4 ? 3 * hi : hi));
 			const int sl = wrp < 3 ? hi : (wrp == 3 ? 1 + hi : (wrp == 4 ? 2 * hi : 2));
 			const int hc = ((cx & 3) << 4) | (lane & 15);
-			const int n = p2 ? sm.cnt[hc] : 0;
-			const int st = cell_start(hc);
-			__syncthreads();  // B2: idx complete, every warp has read the cell counts
-			if(tid < 64) sm.cnt[tid] = 0;  // for the next chunk / block (ordered by the barriers below)
+			int n, st;
+			if constexpr(SORTED) {
+				// the bucket is cell-major, so the staged slots of this chunk are already grouped by home cell: cell hc owns the
+				// slots [offs[hc], offs[hc + 1]) - c0, clipped to the chunk.  No counting sort, no index array, no second barrier.
+				const int lo = min(max((int) sm.offs[hc] - c0, 0), nchunk), hiE = min(max((int) sm.offs[hc + 1] - c0, 0), nchunk);
+				st = lo;
+				n = p2 ? hiE - lo : 0;
+			} else {
+				// exclusive scan of the 64 cell counts, redundantly in every warp (lane l holds cells 2l and 2l+1): no barrier,
+				// no shared prefix array
+				const int c0v = sm.cnt[2 * lane], c1v = sm.cnt[2 * lane + 1];
+				int excl = c0v + c1v;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1) {
+					const int t = __shfl_up_sync(0xffffffffu, excl, o);
+					if(lane >= o) excl += t;
+				}
+				excl -= c0v + c1v;
+				auto cell_start = [&](int h) {  // every lane of the warp must call it
+					const int e = __shfl_sync(0xffffffffu, excl, h >> 1), c = __shfl_sync(0xffffffffu, c0v, h >> 1);
+					return e + ((h & 1) ? c : 0);
+				};
+				{
+					const int s0 = cell_start(max(cr0, 0) >> 16), s1 = cell_start(max(cr1, 0) >> 16), s2 = cell_start(max(cr2, 0) >> 16);
+					// (the swizzled record slot is stored: phase 2 reads it three times per particle, once per x-slice)
+					if(cr0 >= 0) sm.idx[s0 + (cr0 & 0xffff)] = (unsigned short) rec_slot(tid);
+					if(cr1 >= 0) sm.idx[s1 + (cr1 & 0xffff)] = (unsigned short) rec_slot(T + tid);
+					if(cr2 >= 0) sm.idx[s2 + (cr2 & 0xffff)] = (unsigned short) rec_slot(2 * T + tid);
+				}
+				n = p2 ? sm.cnt[hc] : 0;
+				st = cell_start(hc);
+				__syncthreads();  // B2: idx complete, every warp has read the cell counts
+				if(tid < 64) sm.cnt[tid] = 0;  // for the next chunk / block (ordered by the barriers below)
+			}
 			{
 				float pa, pb, pc;
 				bspline_poly(sl, pa, pb, pc);
@@ -626,12 +636,8 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 #pragma unroll
 				for(int n9 = 0; n9 < 9; ++n9) acc01[n9] = acc23[n9] = mk2(0.f, 0.f);
 				const f2 c01 = mk2(0.f, 1.f);
-#ifdef CB200_ABLATE_P2   // timing experiment only (results are wrong): what does the cell-parallel accumulation cost end to end?
-				for(int p = 0; p < 0; ++p) {
-#else
 				for(int p = 0; p < n; ++p) {  // (requesting the next particle's index / first quad one iteration ahead measured 0.8 % slower)
-#endif
-					const int slot = sm.idx[st + p];
+					const int slot = SORTED ? rec_slot(st + p) : (int) sm.idx[st + p];
 					const float4 r0 = sm.rec[0][slot];  // (y, z, x, code)
 					if(__float_as_int(r0.w) & (kRecMover | kRecDrop)) continue;
 					const float4 r1 = sm.rec[1][slot], r2 = sm.rec[2][slot], r3 = sm.rec[3][slot];

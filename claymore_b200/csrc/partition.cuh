@@ -115,7 +115,7 @@ __global__ void scan_inverse_kernel(int num, const int* map, int* map_inv) {
 // dst_block lets the caller write straight into the compacted numbering (fuses update_buckets, :979-1000).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBucketThreads = 128;
-__device__ __forceinline__ int flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst, int* s_prefix) {
+__device__ __forceinline__ int flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst, int* s_prefix, unsigned short* __restrict__ offs = nullptr) {
 	const int tid = threadIdx.x, lane = tid & 31;
 	if(tid < 32) {
 		const int2 c = reinterpret_cast<const int2*>(cell_counts_blk)[lane];
@@ -132,6 +132,7 @@ __device__ __forceinline__ int flatten_block(const Cfg& cfg, const int* __restri
 	}
 	__syncthreads();
 	const int total = s_prefix[64];
+	if(offs && tid < 64) offs[tid] = (unsigned short) s_prefix[tid];  // where the cells start inside the cell-major bucket (read by g2p2g's phase 2)
 	for(int i = tid; i < total; i += kBucketThreads) {
 		int c = 0;
 #pragma unroll
@@ -143,10 +144,10 @@ __device__ __forceinline__ int flatten_block(const Cfg& cfg, const int* __restri
 	return total;
 }
 
-__global__ void __launch_bounds__(kBucketThreads) cell_bucket_to_block_kernel(Cfg cfg, int block_count, const int* cell_particle_counts, const int* cellbuckets, int* particle_bucket_sizes, int* buckets) {
+__global__ void __launch_bounds__(kBucketThreads) cell_bucket_to_block_kernel(Cfg cfg, int block_count, const int* cell_particle_counts, const int* cellbuckets, int* particle_bucket_sizes, int* buckets, unsigned short* cell_offsets = nullptr) {
 	__shared__ int s_prefix[65];
 	for(int b = blockIdx.x; b < block_count; b += gridDim.x) {
-		const int total = flatten_block(cfg, cell_particle_counts + (size_t) b * kBlockVol, cellbuckets + ((size_t) b << cfg.ppb_shift), buckets + ((size_t) b << cfg.ppb_shift), s_prefix);
+		const int total = flatten_block(cfg, cell_particle_counts + (size_t) b * kBlockVol, cellbuckets + ((size_t) b << cfg.ppb_shift), buckets + ((size_t) b << cfg.ppb_shift), s_prefix, cell_offsets ? cell_offsets + (size_t) b * kBlockVol : nullptr);
 		if(threadIdx.x == 0) particle_bucket_sizes[b] += total;
 	}
 }
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kSummaryThreads) summary_kernel(const SummaryA
 // one WARP per old block: the 64 cell counts are prefix-summed with shuffles, a tag finds its cell by a 6-step binary
 // search over the lane-distributed prefix (shuffles, no shared memory, no block barrier), so the eight warps of a CTA
 // stream independent blocks and hide each other's latency.
-__device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst) {
+__device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __restrict__ cell_counts_blk, const int* __restrict__ cellbuckets_blk, int* __restrict__ dst, unsigned short* __restrict__ offs) {
 	const int lane = threadIdx.x & 31;
 	const int2 c = reinterpret_cast<const int2*>(cell_counts_blk)[lane];
 	const int pair = c.x + c.y;
@@ -312,6 +313,7 @@ __device__ __forceinline__ int warp_flatten_block(const Cfg& cfg, const int* __r
 	const int p_even = inc - pair;       // exclusive prefix of cell 2*lane
 	const int p_odd = p_even + c.x;      // exclusive prefix of cell 2*lane + 1
 	const int total = __shfl_sync(0xffffffffu, inc, 31);
+	if(offs) reinterpret_cast<ushort2*>(offs)[lane] = make_ushort2((unsigned short) p_even, (unsigned short) p_odd);  // cell starts inside the bucket
 #pragma unroll 2
 	for(int i0 = 0; i0 < total; i0 += 32) {
 		const int i = i0 + lane;
@@ -347,8 +349,9 @@ struct RebuildArgs {
 	int* dst_sizes[kMaxModels];          // cur buffers (new numbering)
 	int* dst_buckets[kMaxModels];
 	int* bin_offsets[kMaxModels];        // cur buffers: exclusive scan of the bin demand
+	unsigned short* dst_offs[kMaxModels];  // cur buffers (new numbering): start of every cell inside the cell-major block bucket
 };
-__global__ void __launch_bounds__(kRebuildThreads) rebuild_kernel(const RebuildArgs a) {
+__global__ void __launch_bounds__(kRebuildThreads, 2) rebuild_kernel(const RebuildArgs a) {  // 2 CTAs/SM: the gather rounds of a marked block are latency bound
 	constexpr int PER_WARP = kRebuildTile / (kRebuildThreads / 32);
 	static_assert(kRebuildTile == 64, "the tile scan below is written for two warps");
 	__shared__ int s_tot[kMaxModels][kRebuildTile];
@@ -405,7 +408,8 @@ __global__ void __launch_bounds__(kRebuildThreads) rebuild_kernel(const RebuildA
 				}
 				continue;
 			}
-			const int total = warp_flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift));
+			const int total = warp_flatten_block(cfg, a.cell_counts[m] + (size_t) b * kBlockVol, a.cellbuckets[m] + ((size_t) b << cfg.ppb_shift), a.dst_buckets[m] + ((size_t) nb << cfg.ppb_shift),
+			                                     a.dst_offs[m] ? a.dst_offs[m] + (size_t) nb * kBlockVol : nullptr);
 			if(lane == 0) {
 				a.dst_sizes[m][nb] = total;
 				a.bin_offsets[m][nb] = tp[1 + m] + s_pre[1 + m][t] + (t >= 32 ? s_half[1 + m] : 0);
