@@ -166,6 +166,33 @@ private:
 	std::map<std::string, void*> map_;
 };
 IpcCache g_ipc;
+
+// pinned StepState mirrors are recycled: cudaMallocHost / cudaFreeHost are page-locking system calls (milliseconds), paid per
+// simulator otherwise
+class PinnedStates {
+public:
+	cudaError_t get(StepState** p) {
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			if(!free_.empty()) {
+				*p = free_.back();
+				free_.pop_back();
+				return cudaSuccess;
+			}
+		}
+		return cudaMallocHost(p, sizeof(StepState));
+	}
+	void put(StepState* p) {
+		if(!p) return;
+		std::lock_guard<std::mutex> g(mu_);
+		free_.push_back(p);
+	}
+
+private:
+	std::mutex mu_;
+	std::vector<StepState*> free_;
+};
+PinnedStates g_pinned;
 template<typename T>
 cudaError_t pool_alloc(T** p, size_t bytes) { return g_pool.alloc(reinterpret_cast<void**>(p), bytes); }
 
@@ -823,7 +850,7 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 	const size_t mb = (size_t) desc->max_blocks;
 	CK(pool_alloc(&s->d_state, sizeof(StepState)));
 	CK(cudaMemsetAsync(s->d_state, 0, sizeof(StepState), s->stream));
-	CK(cudaMallocHost(&s->h_state, sizeof(StepState)));
+	CK(g_pinned.get(&s->h_state));
 	memset(s->h_state, 0, sizeof(StepState));
 	for(int i = 0; i < 2; ++i) {
 		int e = alloc_partition(s, s->part[i]);
@@ -907,8 +934,8 @@ int cb200_sim_destroy(cb200_sim* s) {
 		g_pool.release(s->halo_list[i]);
 		g_pool.release(s->interior_list[i]);
 	}
-	cudaFreeHost(s->h_state);
-	if(s->h_poll) cudaFreeHost(s->h_poll);
+	g_pinned.put(s->h_state);
+	g_pinned.put(s->h_poll);
 	if(s->poll_event) cudaEventDestroy(s->poll_event);
 	if(s->owns_stream) cudaStreamDestroy(s->stream);
 	delete s;
@@ -1154,7 +1181,7 @@ static int poll_capacity(cb200_sim* s) {
 	if(!s->poll_pending && ++s->steps_since_poll >= 16) {
 		s->steps_since_poll = 0;
 		if(!s->h_poll) {
-			CK(cudaMallocHost(&s->h_poll, sizeof(StepState)));
+			CK(g_pinned.get(&s->h_poll));
 			CK(cudaEventCreateWithFlags(&s->poll_event, cudaEventDisableTiming));
 		}
 		CK(cudaMemcpyAsync(s->h_poll, s->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s->stream));

@@ -109,7 +109,12 @@ __global__ void __launch_bounds__(256) rasterize_blocks_kernel(Cfg cfg, int mate
 		if(threadIdx.x < 8) s_bno[threadIdx.x] = table_query(cfg, table, kx + ((threadIdx.x >> 2) & 1), ky + ((threadIdx.x >> 1) & 1), kz + (threadIdx.x & 1));
 		__syncthreads();
 		const float* bins = pb.bins + (size_t) pb.bin_offsets[b] * binf;
-		for(int i = threadIdx.x; i < n; i += blockDim.x) {
+		// the bucket is cell-major: neighbouring lanes would hold particles of one cell and fight over the same 27 nodes (a shared float
+		// atomicAdd is a compare-and-swap loop).  A lane takes every (n/32)-th particle instead, so a warp's lanes sit in different cells.
+		const int per_lane = (n + 31) >> 5;
+		for(int t = threadIdx.x; t < per_lane * 32; t += blockDim.x) {
+			const int i = (t & 31) * per_lane + (t >> 5);
+			if(i >= n) continue;
 			const float* bin = bins + (size_t) (i >> 5) * binf + (i & 31);
 			int ab[3];
 			float w[3][3];
