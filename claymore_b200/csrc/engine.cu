@@ -834,10 +834,22 @@ int cb200_sim_capacity(cb200_sim* s, int* max_blocks, int* grow_events) {
 	return 0;
 }
 
+static int sim_create_impl(cb200_sim* s, const cb200_sim_desc* desc, void* stream);
+
 int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) {
 	if(!desc || !out || !cfg_valid(desc->cfg) || desc->max_blocks <= 0) return (int) cudaErrorInvalidValue;
 	preload_kernels();
 	cb200_sim* s = new cb200_sim();
+	const int e = sim_create_impl(s, desc, stream);
+	if(e) {  // give back whatever was allocated before the failing call (every pointer of the struct starts out null)
+		cb200_sim_destroy(s);
+		return e;
+	}
+	*out = s;
+	return 0;
+}
+
+static int sim_create_impl(cb200_sim* s, const cb200_sim_desc* desc, void* stream) {
 	s->desc = *desc;
 	if(s->desc.mgsp_world < 1) s->desc.mgsp_world = 1;
 	s->cfg = make_cfg(desc->cfg);
@@ -888,7 +900,6 @@ int cb200_sim_create(const cb200_sim_desc* desc, void* stream, cb200_sim** out) 
 		}
 		CK(cudaStreamSynchronize(s->stream));
 	}
-	*out = s;
 	return 0;
 }
 

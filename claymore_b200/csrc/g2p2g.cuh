@@ -769,6 +769,7 @@ __global__ void __launch_bounds__(kG2P2GThreads, CB200_G2P2G_MIN_CTAS) g2p2g_ker
 						mask &= mask - 1;
 						const int rb = a.peer_bno[(size_t) p * a.peer_stride + bno];
 						if(rb >= 0) tma_reduce_add_f32(a.peer_grid[p] + (size_t) rb * kGridBlockFloats, sm.acc + ft * 256, 1024);
+						else if(a.error) atomicOr(a.error, kErrHaloMap);  // tagged as shared but the peer's block number is unknown: never silently drop a halo sum
 					}
 				}
 			}

@@ -160,7 +160,7 @@ typedef struct cb200_sim_stats {
 	int particle_block_count, neighbor_block_count, exterior_block_count;
 	int bin_count[8];
 	float dt, next_dt, max_vel, step_time;
-	int error;               /* 0 ok; bit0 block capacity, bit1 bin capacity, bit2 lost particle, bit3 cell overflow */
+	int error;               /* 0 ok; bit0 block capacity, bit1 bin capacity, bit2 lost particle, bit3 cell overflow, bit4 MGSP halo map inconsistent */
 	long long steps;
 } cb200_sim_stats;
 
