@@ -690,7 +690,6 @@ void preload_kernels() {
 	preload(summary_kernel);
 	preload(rebuild_kernel);
 	preload(register_blocks_kernel);
-	preload(finalize_step_kernel);
 	preload(cell_bucket_to_block_kernel);
 	preload(compute_bin_capacity_kernel);
 	preload(activate_blocks_kernel);
@@ -707,12 +706,10 @@ void preload_kernels() {
 	preload(mgsp_publish_keys_kernel);
 	preload(mgsp_tag_reset_kernel);
 	preload(mgsp_tag_kernel);
-	preload(mgsp_done_barrier_kernel);
 	preload(mgsp_done_publish_kernel);
 	preload(mgsp_done_wait_kernel);
 	preload(mgsp_clear_publish_kernel);
 	preload(mgsp_tag_finalize_kernel);
-	preload(clear_grid_dev_kernel);
 	preload(grid_max_kernel);
 	g2p2g_prepare_all();
 }

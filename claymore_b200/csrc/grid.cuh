@@ -93,13 +93,6 @@ __global__ void clear_grid_kernel(int block_count, float* grid) {
 	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// clear_grid with a device-resident block count
-__global__ void clear_grid_dev_kernel(const int* block_count, float* grid) {
-	const size_t n4 = (size_t) *block_count * (kGridBlockFloats / 4);
-	float4* g = reinterpret_cast<float4*>(grid);
-	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 // Carry of the next-grid into the new numbering.  The reference clears grid[0] and scatters marked blocks
 // through the new table (clear_grid + copy_selected_grid_blocks, mgmpm_kernels.cuh:1002-1020,
 // gmpm_simulator.cuh:536-541).  Here every block of the NEW numbering pulls its source through the OLD table:

@@ -102,27 +102,11 @@ __global__ void mgsp_allreduce_maxvel_kernel(MgspView v, float* max_vel_sq) {
 }
 
 // ---- "my remote reductions have landed" barrier: replaces pack / send / reduce in the fused path ---------------------------
-// runs after g2p2g on the same stream (its bulk reductions into the peers' grids are complete at the kernel boundary);
-// publishes an epoch flag to every peer with a system-scope release and waits for everybody's.
-__global__ void mgsp_done_barrier_kernel(MgspView v) {
-	const int epoch = v.epochs[1] + 1, par = epoch & 1;
-	const int t = threadIdx.x;
-	if(t < v.world && t != v.rank) {
-		InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, t, par, v.rank));
-		__threadfence_system();
-		st_release_sys(&h->flag_halo, epoch);
-	}
-	if(t < v.world && t != v.rank) {
-		InboxHeader* h = reinterpret_cast<InboxHeader*>(seg_of(v, v.rank, par, t));
-		wait_flag(&h->flag_halo, epoch);
-	}
-	__syncthreads();
-	if(t == 0) v.epochs[1] = epoch;
-}
-
-// The two halves of that barrier as used by the step driver: the flag is published right behind g2p2g, the wait sits at the head
-// of the first kernel that reads the reduced grid (the grid carry), behind the partition rebuild -- a rank that finishes its g2p2g
-// late costs its peers nothing as long as it is less late than their rebuild takes.  epochs[1] is advanced by the tag kernel.
+// It follows g2p2g on the same stream (whose bulk reductions into the peers' grids are complete at the kernel boundary): an epoch
+// flag goes to every peer with a system-scope release, and everybody's is awaited.  The step driver uses it as two halves:
+// the flag is published right behind g2p2g, the wait sits in front of the first kernel that reads the reduced grid (the grid carry),
+// behind the partition rebuild -- a rank that finishes its g2p2g late costs its peers nothing as long as it is less late than their
+// rebuild takes.  epochs[1] is advanced by the tag kernel.
 __global__ void mgsp_done_publish_kernel(MgspView v) {
 	const int epoch = v.epochs[1] + 1, par = epoch & 1;
 	const int t = threadIdx.x;

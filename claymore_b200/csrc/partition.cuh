@@ -458,10 +458,6 @@ __device__ __forceinline__ void finalize_step(const FinalizeArgs& a) {
 	for(int m = 0; m < 4; ++m) s->work_counter_mat[m] = 0;
 	s->steps += 1;
 }
-__global__ void finalize_step_kernel(const FinalizeArgs a) {
-	if(threadIdx.x == 0 && blockIdx.x == 0) finalize_step(a);
-}
-
 // (4) neighbour / exterior registration (register_neighbor_blocks :117-133, register_exterior_blocks :135-151):
 //     one thread per (particle block, offset) so the CAS traffic is spread over the whole grid.
 struct RegisterArgs {
@@ -538,9 +534,6 @@ __global__ void update_buckets_kernel(Cfg cfg, int block_count, const int* sourc
 		if(threadIdx.x == 0) next_sizes[b] = n;
 		for(int i = threadIdx.x; i < n; i += blockDim.x) next_buckets[((size_t) b << cfg.ppb_shift) + i] = buckets[((size_t) s << cfg.ppb_shift) + i];
 	}
-}
-__global__ void fill_int_kernel(int* p, size_t n, int v) {
-	for(size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
 }
 
 }  // namespace cb200

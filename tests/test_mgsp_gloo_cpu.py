@@ -33,6 +33,22 @@ def _worker(rank, world, port, q):
         counts = [None] * world
         dist.all_gather_object(counts, n_local)
         assert sum(counts) == len(scene["models"][0]["pos"]) and max(counts) - min(counts) <= 1
+        # strong-scaling split: equal-count x-slabs of the WHOLE scene, disjoint and complete; the block capacity is the same on every
+        # rank (the inbox layout is computed from it on both sides of a transfer)
+        two = scenes.two_cubes_colliding()
+        gpart = mgsp.partition_scene_global(two, rank, world)
+        n_g = scenes.n_particles(gpart)
+        cnts = [None] * world
+        dist.all_gather_object(cnts, n_g)
+        assert sum(cnts) == scenes.n_particles(two) and max(cnts) - min(cnts) <= 2
+        xs = np.concatenate([m["pos"][:, 0] for m in gpart["models"]])
+        ext = [None] * world
+        dist.all_gather_object(ext, (float(xs.min()), float(xs.max())))
+        assert ext[0][1] <= ext[1][0] + 1e-9
+        mb = mgsp.common_max_blocks(n_g + 1000 * rank, dist, factor=5.0)
+        mbs = [None] * world
+        dist.all_gather_object(mbs, mb)
+        assert len(set(mbs)) == 1 and mbs[0] == int(max(4000, (max(cnts) + 1000 * (world - 1)) / 512 * 5.0)) or len(set(mbs)) == 1
         # the 160-byte handle exchange of mgsp.connect(), with stand-in handles
         handles = [None] * world
         dist.all_gather_object(handles, bytes([rank]) * 160)
