@@ -106,9 +106,9 @@ def apply_material(sim, model_id, material, dx):
     getattr(sim, name)(*args, model=model_id)
 
 
-def build_engine(scene, dt=1e-4, max_blocks=4000, max_ppc=128, use_graph=True, fps=0, **kw):
+def build_engine(scene, dt=1e-4, max_blocks=4000, max_ppc=128, use_graph=True, fps=0, cfl=0.5, **kw):
     from .simulator import GmpmSimulator
-    cfg = Config(domain_bits=scene["domain_bits"], max_ppc=max_ppc)
+    cfg = Config(domain_bits=scene["domain_bits"], max_ppc=max_ppc, cfl=cfl)
     sim = GmpmSimulator(dt=dt, fps=fps, config=cfg, max_blocks=max_blocks, use_graph=use_graph, **kw)
     dx = 1.0 / (1 << scene["domain_bits"])
     for m in scene["models"]:

@@ -411,3 +411,32 @@ def test_mgsp_multiprocess_matches_single_gpu(cuda_lib, world, split):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-4000:]
     assert "MGSP_PARITY_OK" in r.stdout, r.stdout[-4000:]
+
+
+def test_particle_moving_more_than_one_cell_is_dropped_like_the_reference(oracle, cuda_lib):
+    """SURVEY.md Appendix B #4 (mgmpm_kernels.cuh:881-885): a particle whose new stencil leaves the 2x2x2 arena of its block keeps
+    its state and its bucket entry, but its P2G contribution is lost.  Unreachable with cfl <= 1, so the test raises the CFL factor
+    to 2.3 cells per sub-step: about a third of the cube's mass is missing from the grid, identically in the oracle and on the device,
+    and the device reports it (error bit 2, kErrLostParticle)."""
+    scene = scenes.small_cube(v0=(-3.0, 0.0, 0.0))
+    osim = scenes.build_oracle(oracle, scene, dt=1e-1, cfl=2.3)
+    esim = scenes.build_engine(scene, dt=1e-1, cfl=2.3, auto_grow=False)
+    total = scenes.n_particles(scene) * 1e3 * (1.0 / 64) ** 3 / 8
+    for k in range(3):
+        osim.step(1)
+        esim.step(1)
+        st = esim.stats()
+        assert (st.particle_block_count, st.neighbor_block_count, st.exterior_block_count) == osim.block_counts()
+        oh, og = scenes.grid_by_key(osim.active_keys(), osim.grid())
+        eh, eg = scenes.grid_by_key(esim.active_keys(), esim.grid())
+        assert np.array_equal(oh, eh)
+        mo, me = og[:, 0].sum(dtype=np.float64), eg[:, 0].sum(dtype=np.float64)
+        assert mo < 0.8 * total, "the scene must actually drop contributions"
+        assert abs(me - mo) <= 1e-5 * mo, (k, me, mo)
+        # dt is 20x the elastic time step here: rounding differences grow by ~15x per sub-step (measured 3e-6, 4e-6, 7e-5 of the peak)
+        assert np.abs(eg[:, 0] - og[:, 0]).max() <= 3e-4 * og[:, 0].max()
+        assert np.abs(eg[:, 1:] - og[:, 1:]).max() <= 2e-3 * np.abs(og[:, 1:]).max()
+    assert esim.stats().error & 4
+    # nothing is lost from the particle set itself
+    assert len(esim.retrieve(0)) == scenes.n_particles(scene)
+    esim.close()
