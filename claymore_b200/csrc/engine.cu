@@ -740,9 +740,14 @@ template<typename T>
 int grow_array(cb200_sim* s, T*& p, size_t old_elems, size_t new_elems, int fill_byte) {
 	T* q = nullptr;
 	CK(pool_alloc(&q, new_elems * sizeof(T)));
-	if(p && old_elems) CK(cudaMemcpyAsync(q, p, old_elems * sizeof(T), cudaMemcpyDeviceToDevice, s->stream));
-	if(new_elems > old_elems) CK(cudaMemsetAsync(q + old_elems, fill_byte, (new_elems - old_elems) * sizeof(T), s->stream));
-	CK(cudaStreamSynchronize(s->stream));
+	int e = 0;
+	if(p && old_elems) e = (int) cudaMemcpyAsync(q, p, old_elems * sizeof(T), cudaMemcpyDeviceToDevice, s->stream);
+	if(!e && new_elems > old_elems) e = (int) cudaMemsetAsync(q + old_elems, fill_byte, (new_elems - old_elems) * sizeof(T), s->stream);
+	if(!e) e = (int) cudaStreamSynchronize(s->stream);
+	if(e) {
+		g_pool.release(q);
+		return e;
+	}
 	g_pool.release(p);
 	p = q;
 	return 0;
@@ -751,16 +756,17 @@ int grow_array(cb200_sim* s, T*& p, size_t old_elems, size_t new_elems, int fill
 
 extern "C" {
 
-// In-place growth of the block capacity between sub-steps: what GmpmSimulator::check_capacity + the resize calls of main_loop do
-// (gmpm_simulator.cuh:283-300, 371-376, 404-411, 528-548), except that every live array keeps its contents (the reference
-// resizes the *next* buffers, whose contents are dead at that point of its loop; here the call may come at any sub-step
-// boundary).  The sub-step graphs are re-captured on the next step.
 void cb200_default_material(const cb200_config* cfg, int material, cb200_particle_buffer* out) {
 	if(!cfg || !out) return;
 	memset(out, 0, sizeof(*out));
 	default_material(*cfg, material, *out);
 }
 
+// In-place growth of the block capacity between sub-steps: what GmpmSimulator::check_capacity + the resize calls of main_loop do
+// (gmpm_simulator.cuh:283-300, 371-376, 404-411, 528-548), except that every live array keeps its contents (the reference
+// resizes the *next* buffers, whose contents are dead at that point of its loop; here the call may come at any sub-step
+// boundary).  The sub-step graphs are re-captured on the next step.
+// A failure part-way (out of memory) leaves a valid simulator at the old capacity: arrays already moved are merely larger.
 int cb200_sim_reserve(cb200_sim* s, int new_max_blocks) {
 	if(!s || new_max_blocks <= 0) return (int) cudaErrorInvalidValue;
 	if(new_max_blocks <= s->desc.max_blocks) return 0;
