@@ -39,7 +39,7 @@ BYTES_BY_MATERIAL = {0: 40.0, 1: 104.0, 2: 112.0, 3: 112.0}   # algorithmic byte
 MATERIAL_NAMES = {0: "J_FLUID", 1: "FIXED_COROTATED", 2: "SAND", 3: "NACC"}
 # CPU-arm sample of a workload: same geometry / grid / material / dt with the length scale reduced until the oracle port finishes
 # a sub-step in about a second
-CPU_SAMPLES = {"spheres40m": ("two_spheres", dict(domain_bits=9, radius=0.1645 / 4), "two elastic spheres (fixed-corotated), 512^3 grid, r=21 cells"),
+CPU_SAMPLES = {"spheres40m": ("two_spheres", dict(domain_bits=9, radius=0.1645 / 2), "two elastic spheres (fixed-corotated), 512^3 grid, r=42 cells"),
                "spheres5m": ("two_spheres", dict(domain_bits=8, radius=0.1645 / 2), "two elastic spheres (fixed-corotated), 256^3 grid, r=21 cells"),
                "sand20m": ("sand_column", dict(domain_bits=9, size=(40, 60, 40)), "sand column (Drucker-Prager), 512^3 grid, 40x60x40 cells"),
                "fluid40m": ("fluid_dam", dict(domain_bits=10, size=(50, 32, 50)), "fluid dam, 1024^3 grid, 50x32x50 cells"),
