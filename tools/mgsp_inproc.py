@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Debug aid: N MGSP ranks inside ONE process on ONE GPU (peers wired with set_peers instead of CUDA IPC), global x-slab split of a
-named workload, K sub-steps, then the union of the shards against a single-domain engine run.  Usable under compute-sanitizer.
+named workload, K sub-steps, then the union of the shards against a single-domain engine run.  Not under compute-sanitizer: it
+serialises kernel launches, and the ranks' flag waits need their peers' kernels to run concurrently (the run hangs).
     python tools/mgsp_inproc.py --workload spheres640k --ranks 4 --steps 20 [--split global|model|2x2]"""
 import argparse
 import os
